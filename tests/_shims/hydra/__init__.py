@@ -1,0 +1,1 @@
+"""Minimal stand-in for hydra (test-only)."""

@@ -1,0 +1,2 @@
+def calculate_frechet_distance(*a, **k):
+    raise NotImplementedError

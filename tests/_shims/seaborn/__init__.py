@@ -1,0 +1,2 @@
+def color_palette(*a, **k):
+    return [(0.0, 0.0, 0.0)] * 64

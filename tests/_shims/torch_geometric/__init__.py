@@ -1,0 +1,1 @@
+"""Minimal stand-in for torch_geometric (test-only)."""

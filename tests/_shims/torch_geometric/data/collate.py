@@ -1,0 +1,2 @@
+def collate(*a, **k):
+    raise NotImplementedError

@@ -1,0 +1,6 @@
+from typing import Any
+IndexType = Any
+
+
+class Dataset:
+    pass

@@ -1,0 +1,2 @@
+def makedirs(*a, **k):
+    return None

@@ -1,0 +1,3 @@
+class DataLoader:
+    def __init__(self, *a, **k):
+        raise NotImplementedError

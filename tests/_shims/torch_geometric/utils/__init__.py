@@ -1,0 +1,26 @@
+import torch
+
+
+def to_dense_batch(x, batch=None, fill_value=0.0, max_num_nodes=None, batch_size=None):
+    """Dense (B, Nmax, *) tensor + validity mask from a PyG-style (x, batch) pair."""
+    if batch is None:
+        batch = x.new_zeros(x.size(0), dtype=torch.long)
+    if batch_size is None:
+        batch_size = int(batch.max()) + 1 if batch.numel() else 0
+    num_nodes = torch.zeros(batch_size, dtype=torch.long).scatter_add_(
+        0, batch, torch.ones_like(batch))
+    cum = torch.cat([num_nodes.new_zeros(1), num_nodes.cumsum(0)])
+    if max_num_nodes is None:
+        max_num_nodes = int(num_nodes.max()) if batch_size else 0
+    idx = torch.arange(batch.size(0)) - cum[batch] + batch * max_num_nodes
+    size = [batch_size * max_num_nodes] + list(x.size())[1:]
+    out = x.new_full(size, fill_value)
+    out[idx] = x
+    out = out.view([batch_size, max_num_nodes] + list(x.size())[1:])
+    mask = torch.zeros(batch_size * max_num_nodes, dtype=torch.bool)
+    mask[idx] = True
+    return out, mask.view(batch_size, max_num_nodes)
+
+
+def to_dense_adj(*a, **k):
+    raise NotImplementedError("to_dense_adj is not on the sampling path")
