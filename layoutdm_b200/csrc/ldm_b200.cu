@@ -1,0 +1,590 @@
+// C-ABI implementation (include/ldm_b200.h): handle, weight repacking, TMA descriptors and the per-step launch
+// sequence of the LayoutDM denoising loop.  CUDA runtime only (the driver's cuTensorMapEncodeTiled is fetched
+// through cudaGetDriverEntryPoint, so there is no link-time libcuda dependency) and no torch types.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/ldm_b200.h"
+#include "attention.cuh"
+#include "common.cuh"
+#include "embed.cuh"
+#include "gemm_tc.cuh"
+#include "posterior_sample.cuh"
+
+using namespace ldm;
+
+namespace {
+
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) return fail(LDM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+constexpr int kMaxLayers = 16;
+constexpr int kHeadPad = 64;        // per-head width after padding 58 -> 64
+constexpr int kQkvN = 3 * 8 * kHeadPad;   // 1536
+constexpr int kLogitLd = 160;       // padded logits row (C <= 160)
+constexpr int kFF1Tile = 232;       // FF1 N tile (1856 = 8 * 232), computed as UMMA_N = 240
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int load_encode() {
+  if (g_encode) return LDM_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return fail(LDM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return LDM_OK;
+}
+
+// 2-D row-major [rows][cols] 16-bit tensor, box = box_rows x 64 columns, 128-byte swizzle, zero OOB fill.
+int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, bool bf16) {
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LDM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box_rows=%u", (int)r,
+                                     (unsigned long long)rows, (unsigned long long)cols, box_rows);
+  return LDM_OK;
+}
+
+// (B,S,C) contiguous <-> padded internal logits [B*128][160]
+__global__ void logits_scatter_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_layouts, int S, int C) {
+  const size_t n = static_cast<size_t>(n_layouts) * S * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C); const size_t tok = i / C; const int s = static_cast<int>(tok % S); const size_t b = tok / S;
+    dst[(b * 128 + s) * kLogitLd + c] = src[i];
+  }
+}
+__global__ void logits_gather_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_layouts, int S, int C) {
+  const size_t n = static_cast<size_t>(n_layouts) * S * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C); const size_t tok = i / C; const int s = static_cast<int>(tok % S); const size_t b = tok / S;
+    dst[i] = src[(b * 128 + s) * kLogitLd + c];
+  }
+}
+__global__ void fill_ids_kernel(long long* dst, long long v, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) dst[i] = v;
+}
+
+}  // namespace
+
+struct LdmHandle {
+  LdmModelDesc desc;
+  int C = 0, S = 0, L = 0, T = 0, G = 0;
+  bool bf16 = false;
+  int num_sms = 148;
+  int64_t launches = 0;
+  int debug_stop_after = 0;   // test tap: stop the denoiser after this many launches (0 = run everything)
+  // parameters (device)
+  float *cat_emb = nullptr, *pos = nullptr, *adaln = nullptr, *sched = nullptr;
+  void *wqkv[kMaxLayers] = {}, *wo[kMaxLayers] = {}, *w1[kMaxLayers] = {}, *w2[kMaxLayers] = {}, *whead = nullptr;
+  float *bqkv[kMaxLayers] = {}, *bo[kMaxLayers] = {}, *b1[kMaxLayers] = {}, *b2[kMaxLayers] = {}, *ln2w[kMaxLayers] = {}, *ln2b[kMaxLayers] = {};
+  float *hlnw = nullptr, *hlnb = nullptr;
+  CUtensorMap m_wqkv[kMaxLayers], m_wo[kMaxLayers], m_w1[kMaxLayers], m_w2[kMaxLayers], m_whead;
+  // workspace (device), sized for cap layouts
+  int cap = 0;
+  void *x16 = nullptr, *qkv16 = nullptr, *att16 = nullptr, *z16 = nullptr, *hid16 = nullptr;
+  float *x32 = nullptr, *y32 = nullptr, *logits = nullptr;
+  long long* ids[2] = {nullptr, nullptr};
+  long long* ids_final = nullptr;
+  long long *c_seq = nullptr, *c_seq_orig = nullptr; unsigned char* c_mask = nullptr; float* c_tbl = nullptr;  // staging for ldm_sample_host
+  CUtensorMap m_x16, m_att16, m_z16, m_hid16;
+  std::vector<void*> owned;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(LdmHandle* h, T** p, size_t n) {
+  CK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  h->owned.push_back(*p);
+  return LDM_OK;
+}
+template <typename T>
+int dev_upload(LdmHandle* h, T** p, const T* src, size_t n) {
+  int rc = dev_alloc(h, p, n);
+  if (rc) return rc;
+  CK(cudaMemcpy(*p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return LDM_OK;
+}
+
+int pack16(LdmHandle* h, void** dst, const float* src_dev, const int* row_map_dev, int dst_rows, int dst_cols, int src_cols) {
+  CK(cudaMalloc(dst, static_cast<size_t>(dst_rows) * dst_cols * 2));
+  h->owned.push_back(*dst);
+  const int blocks = 512;
+  if (h->bf16) pack_weight_kernel<true><<<blocks, 256>>>(src_dev, *dst, row_map_dev, dst_rows, dst_cols, src_cols);
+  else pack_weight_kernel<false><<<blocks, 256>>>(src_dev, *dst, row_map_dev, dst_rows, dst_cols, src_cols);
+  CK(cudaGetLastError());
+  return LDM_OK;
+}
+
+// util.py:47-70 + constrained.py:64-90: float64 schedule, fp32 log tables, 8 rows of length T+1 per group
+void build_schedule(const LdmModelDesc& d, int N, float* out /*[8][T+1]*/) {
+  const int T = d.num_timesteps, TT = T + 1;
+  std::vector<double> att(T + 1), ctt(T + 1);
+  att[0] = 1.0; ctt[0] = 0.0;
+  for (int i = 0; i < T; ++i) {
+    att[i + 1] = static_cast<double>(i) / (T - 1) * (d.att_T - d.att_1) + d.att_1;
+    ctt[i + 1] = static_cast<double>(i) / (T - 1) * (d.ctt_T - d.ctt_1) + d.ctt_1;
+  }
+  auto l1m = [](double la) { return std::log(1.0 - std::exp(la) + 1e-40); };
+  for (int i = 0; i < TT; ++i) for (int r = 0; r < 8; ++r) out[r * TT + i] = 0.0f;
+  for (int i = 0; i < T; ++i) {
+    const double at = att[i + 1] / att[i];
+    const double ct = 1.0 - (1.0 - ctt[i + 1]) / (1.0 - ctt[i]);
+    const double bt = (1.0 - at - ct) / N;
+    out[0 * TT + i] = static_cast<float>(std::log(at));
+    out[1 * TT + i] = static_cast<float>(std::log(bt));
+    out[2 * TT + i] = static_cast<float>(std::log(ct));
+    out[6 * TT + i] = static_cast<float>(l1m(std::log(ct)));
+  }
+  for (int i = 0; i < TT; ++i) {
+    const double a = (i < T) ? att[i + 1] : 1.0, c = (i < T) ? ctt[i + 1] : 0.0;
+    const double b = (1.0 - a - c) / N;
+    out[3 * TT + i] = static_cast<float>(std::log(a));
+    out[4 * TT + i] = static_cast<float>(std::log(b));
+    out[5 * TT + i] = static_cast<float>(std::log(c));
+    out[7 * TT + i] = static_cast<float>(l1m(std::log(c)));
+  }
+}
+
+template <typename K>
+int set_smem(K kernel, int bytes) {
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return LDM_OK;
+}
+
+int ensure_workspace(LdmHandle* h, int n_layouts) {
+  if (n_layouts <= h->cap) return LDM_OK;
+  // free the old workspace
+  void* olds[] = {h->x16, h->qkv16, h->att16, h->z16, h->hid16, h->x32, h->y32, h->logits, h->ids[0], h->ids[1], h->ids_final, h->c_seq, h->c_seq_orig, h->c_mask};
+  for (void* p : olds) if (p) cudaFree(p);
+  const size_t M = static_cast<size_t>(n_layouts) * kBM;
+  const int d = h->desc.d_model, ff = h->desc.d_ff;
+  CK(cudaMalloc(&h->x16, M * d * 2));
+  CK(cudaMalloc(&h->qkv16, M * kQkvN * 2));
+  CK(cudaMalloc(&h->att16, M * d * 2));
+  CK(cudaMalloc(&h->z16, M * d * 2));
+  CK(cudaMalloc(&h->hid16, M * ff * 2));
+  CK(cudaMalloc(reinterpret_cast<void**>(&h->x32), M * d * 4));
+  CK(cudaMalloc(reinterpret_cast<void**>(&h->y32), M * d * 4));
+  CK(cudaMalloc(reinterpret_cast<void**>(&h->logits), M * kLogitLd * 4));
+  const size_t nid = static_cast<size_t>(n_layouts) * h->S;
+  CK(cudaMalloc(reinterpret_cast<void**>(&h->ids[0]), nid * 8));
+  CK(cudaMalloc(reinterpret_cast<void**>(&h->ids[1]), nid * 8));
+  CK(cudaMalloc(reinterpret_cast<void**>(&h->ids_final), nid * 8));
+  CK(cudaMalloc(reinterpret_cast<void**>(&h->c_seq), nid * 8));
+  CK(cudaMalloc(reinterpret_cast<void**>(&h->c_seq_orig), nid * 8));
+  CK(cudaMalloc(reinterpret_cast<void**>(&h->c_mask), nid));
+  CK(cudaMemset(h->logits, 0, M * kLogitLd * 4));
+  h->cap = n_layouts;
+  int rc;
+  if ((rc = make_map(&h->m_x16, h->x16, M, d, kBM, h->bf16))) return rc;
+  if ((rc = make_map(&h->m_att16, h->att16, M, d, kBM, h->bf16))) return rc;
+  if ((rc = make_map(&h->m_z16, h->z16, M, d, kBM, h->bf16))) return rc;
+  if ((rc = make_map(&h->m_hid16, h->hid16, M, ff, kBM, h->bf16))) return rc;
+  return LDM_OK;
+}
+
+template <bool BF16>
+int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, cudaStream_t st) {
+  const int d = h->desc.d_model, ff = h->desc.d_ff, L = h->L, T = h->T;
+  const int M = n * kBM;
+  const int sms = h->num_sms;
+  {
+    const int warps = n * 128, blocks = (warps * 32 + 255) / 256;
+    embed_adaln_kernel<BF16><<<blocks, 256, 0, st>>>(ids_in, h->cat_emb, h->pos, h->adaln + (static_cast<size_t>(0) * T + t_model) * 2 * d,
+                                                     h->x32, h->x16, n, h->S, d);
+    h->launches++;
+  }
+  int done = 1;
+#define LDM_STAGE_DONE() do { if (h->debug_stop_after && ++done > h->debug_stop_after) { CK(cudaGetLastError()); return LDM_OK; } } while (0)
+  if (h->debug_stop_after == 1) { CK(cudaGetLastError()); return LDM_OK; }
+  for (int l = 0; l < L; ++l) {
+    {  // QKV projection (+bias, q * 1/sqrt(head_dim))
+      GemmParams p{M, kQkvN, d, kQkvN / 256, h->bqkv[l], h->qkv16, kQkvN, 1.0f / sqrtf(static_cast<float>(d / h->desc.n_heads)), 8 * kHeadPad};
+      const int tiles = n * p.n_tiles;
+      gemm_tc_kernel<256, 256, 4, EPI_QKV, BF16><<<std::min(tiles, sms), kGemmThreads, GemmSmem<256, 4>::kBytes, st>>>(h->m_x16, h->m_wqkv[l], p);
+      h->launches++;
+    }
+    LDM_STAGE_DONE();
+    attention_kernel<BF16><<<n * h->desc.n_heads, kAttThreads, kAttSmemBytes, st>>>(h->qkv16, h->att16, h->S, d / h->desc.n_heads, h->desc.n_heads);
+    h->launches++;
+    LDM_STAGE_DONE();
+    {  // out-projection + residual (normalised x) + LayerNorm2
+      GemmLnParams p{M, d, h->bo[l], h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr, h->z16};
+      gemm_ln_kernel<BF16><<<std::min(n, sms), kGemmThreads, kLnSmemBytes, st>>>(h->m_att16, h->m_wo[l], p);
+      h->launches++;
+    }
+    LDM_STAGE_DONE();
+    {  // FF1 + ReLU
+      GemmParams p{M, ff, d, ff / kFF1Tile, h->b1[l], h->hid16, ff, 1.0f, 0};
+      const int tiles = n * p.n_tiles;
+      gemm_tc_kernel<kFF1Tile, 240, 4, EPI_RELU, BF16><<<std::min(tiles, sms), kGemmThreads, GemmSmem<240, 4>::kBytes, st>>>(h->m_z16, h->m_w1[l], p);
+      h->launches++;
+    }
+    LDM_STAGE_DONE();
+    {  // FF2 + residual + (next block's AdaLN | head LayerNorm)
+      GemmLnParams p{};
+      p.M = M; p.K = ff; p.bias = h->b2[l]; p.resid = h->y32; p.y_out = nullptr;
+      if (l + 1 < L) {
+        const float* tab = h->adaln + (static_cast<size_t>(l + 1) * T + t_model) * 2 * d;
+        p.ln_scale = tab; p.ln_shift = tab + d; p.adaln = 1; p.out32 = h->x32; p.out16 = h->x16;
+      } else {
+        p.ln_scale = h->hlnw; p.ln_shift = h->hlnb; p.adaln = 0; p.out32 = nullptr; p.out16 = h->z16;
+      }
+      gemm_ln_kernel<BF16><<<std::min(n, sms), kGemmThreads, kLnSmemBytes, st>>>(h->m_hid16, h->m_w2[l], p);
+      h->launches++;
+    }
+    LDM_STAGE_DONE();
+  }
+  {  // vocabulary head -> fp32 logits
+    GemmParams p{M, kLogitLd, d, 1, nullptr, h->logits, kLogitLd, 1.0f, 0};
+    gemm_tc_kernel<160, 160, 4, EPI_F32, BF16><<<std::min(n, sms), kGemmThreads, GemmSmem<160, 4>::kBytes, st>>>(h->m_z16, h->m_whead, p);
+    h->launches++;
+  }
+  CK(cudaGetLastError());
+  return LDM_OK;
+}
+
+int validate_common(LdmHandle* h, int B, const LdmSampling* s) {
+  if (!h) return fail(LDM_ERR_INVALID, "null handle");
+  if (B <= 0) return fail(LDM_ERR_INVALID, "batch size must be positive (got %d)", B);
+  if (!s) return fail(LDM_ERR_INVALID, "null sampling config");
+  if (s->mode < 0 || s->mode > LDM_SAMPLING_GUMBEL) return fail(LDM_ERR_INVALID, "unknown sampling mode %d (sampling.py:118 raises NotImplementedError)", s->mode);
+  if (s->mode != LDM_SAMPLING_DETERMINISTIC && !(s->temperature > 0.0f)) return fail(LDM_ERR_INVALID, "temperature must be > 0");
+  if (s->mode == LDM_SAMPLING_TOP_P && !(s->top_p > 0.0f && s->top_p <= 1.0f)) return fail(LDM_ERR_INVALID, "top_p must be in (0, 1] (sampling.py:96)");
+  if (s->mode == LDM_SAMPLING_TOP_K && !(s->top_k >= 1 && s->top_k <= h->C)) return fail(LDM_ERR_INVALID, "top_k out of range");
+  return LDM_OK;
+}
+
+int step_impl(LdmHandle* h, int B, const long long* ids_in, int t_model, int t_post, const LdmCond* cond, const LdmSampling* samp,
+              uint64_t seed, uint32_t step_ctr, int64_t b_global0, long long* ids_out, float* logits_out, float* logprob_out,
+              const float* logits_in, const float* logprob_in, cudaStream_t st) {
+  if (t_model < 0 || t_model >= h->T || t_post < 0 || t_post >= h->T)
+    return fail(LDM_ERR_INVALID, "timestep out of range: t_model=%d t_post=%d T=%d (constrained.py:139)", t_model, t_post, h->T);
+  int rc = ensure_workspace(h, B);
+  if (rc) return rc;
+  if (logprob_in == nullptr) {
+    if (logits_in != nullptr) {
+      logits_scatter_kernel<<<1024, 256, 0, st>>>(logits_in, h->logits, B, h->S, h->C);
+      h->launches++;
+    } else {
+      rc = h->bf16 ? launch_denoiser<true>(h, B, ids_in, t_model, st) : launch_denoiser<false>(h, B, ids_in, t_model, st);
+      if (rc) return rc;
+    }
+    if (logits_out != nullptr) {
+      logits_gather_kernel<<<1024, 256, 0, st>>>(h->logits, logits_out, B, h->S, h->C);
+      h->launches++;
+    }
+  }
+  StepParams p{};
+  p.n_layouts = B; p.S = h->S; p.C = h->C; p.n_attr = h->desc.n_attr;
+  p.pad_id = h->C - 2; p.mask_id = h->C - 1;
+  p.constrained = h->desc.q_type == 0;
+  for (int g = 0; g < h->desc.n_attr && g < kMaxAttr; ++g) {
+    p.grp_start[g] = g == 0 ? 0 : h->desc.n_cat + (g - 1) * h->desc.n_bins;
+    p.grp_n[g] = g == 0 ? h->desc.n_cat : h->desc.n_bins;
+  }
+  p.T = h->T; p.t_post = t_post; p.sched = h->sched;
+  p.logits = h->logits; p.ld_logits = kLogitLd; p.logprob_in = logprob_in; p.ids_in = ids_in;
+  if (cond && cond->seq) {
+    p.cond_seq = reinterpret_cast<const long long*>(cond->seq); p.cond_mask = cond->mask;
+    p.cond_seq_orig = reinterpret_cast<const long long*>(cond->seq_orig); p.refine_tbl = cond->refine_table;
+    p.cond_flags = (cond->mask ? COND_HAS_MASK : 0) | (cond->pad_disable ? COND_PAD_DISABLE : 0) |
+                   ((cond->seq_orig && cond->refine_table) ? COND_REFINE : 0);
+  }
+  p.mode = samp->mode; p.temperature = samp->temperature; p.top_p = samp->top_p; p.top_k = samp->top_k;
+  p.seed = seed; p.step_ctr = step_ctr; p.b_global0 = b_global0;
+  p.ids_out = ids_out; p.logprob_out = logprob_out;
+  const int warps = B * h->S, blocks = (warps * 32 + 255) / 256;
+  posterior_sample_kernel<<<blocks, 256, 0, st>>>(p);
+  h->launches++;
+  CK(cudaGetLastError());
+  return LDM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ldm_last_error(void) { return g_err; }
+const char* ldm_version(void) { return "ldm_b200 0.1 (sm_100a, tcgen05)"; }
+
+int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
+  if (!desc || !w || !out) return fail(LDM_ERR_INVALID, "null argument");
+  const int d = desc->d_model, ff = desc->d_ff, L = desc->n_layers, T = desc->num_timesteps;
+  const int C = desc->n_cat + 4 * desc->n_bins + 2, S = desc->n_elem * desc->n_attr;
+  if (d != kD || desc->n_heads != 8 || ff != 8 * kFF1Tile)
+    return fail(LDM_ERR_UNSUPPORTED, "kernels are built for d_model=464, 8 heads, d_ff=1856 (got %d, %d, %d)", d, desc->n_heads, ff);
+  if (L < 1 || L > kMaxLayers || T < 2) return fail(LDM_ERR_UNSUPPORTED, "n_layers must be in [1,%d], T >= 2", kMaxLayers);
+  if (C < 129 || C > kLogitLd || S > 125 || S < 1 || desc->n_attr > kMaxAttr || desc->n_attr < 1)
+    return fail(LDM_ERR_UNSUPPORTED, "vocabulary C=%d must be in [129,160] and S=%d <= 125", C, S);
+  if (desc->q_type != 0 && desc->q_type != 1) return fail(LDM_ERR_INVALID, "q_type must be 0 (constrained) or 1 (vanilla)");
+  if (desc->q_type == 0 && desc->n_attr != 5) return fail(LDM_ERR_UNSUPPORTED, "constrained q_type needs the c-x-y-w-h layout (5 attributes)");
+  CK(cudaSetDevice(desc->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, desc->device));
+  if (prop.major != 10) return fail(LDM_ERR_UNSUPPORTED, "sm_100a kernels need a Blackwell (CC 10.x) device, found CC %d.%d", prop.major, prop.minor);
+  int rc = load_encode();
+  if (rc) return rc;
+
+  LdmHandle* h = new LdmHandle();
+  h->desc = *desc; h->C = C; h->S = S; h->L = L; h->T = T; h->bf16 = desc->operand_dtype == 1;
+  h->G = desc->q_type == 0 ? desc->n_attr : 1;
+  h->num_sms = prop.multiProcessorCount;
+#define TRY(x) do { rc = (x); if (rc) { ldm_destroy(h); return rc; } } while (0)
+
+  TRY(dev_upload(h, &h->cat_emb, w->cat_emb, static_cast<size_t>(C) * d));
+  TRY(dev_upload(h, &h->pos, w->pos_table, static_cast<size_t>(S) * d));
+  TRY(dev_upload(h, &h->hlnw, w->head_ln_w, static_cast<size_t>(d)));
+  TRY(dev_upload(h, &h->hlnb, w->head_ln_b, static_cast<size_t>(d)));
+
+  // AdaLN (scale, shift) for every (layer, t)
+  {
+    float *emb = nullptr, *lw = nullptr, *lb = nullptr;
+    TRY(dev_upload(h, &emb, w->norm1_emb, static_cast<size_t>(L) * T * d));
+    TRY(dev_upload(h, &lw, w->norm1_w, static_cast<size_t>(L) * 2 * d * d));
+    TRY(dev_upload(h, &lb, w->norm1_b, static_cast<size_t>(L) * 2 * d));
+    TRY(dev_alloc(h, &h->adaln, static_cast<size_t>(L) * T * 2 * d));
+    adaln_table_kernel<<<dim3(T, L), 256, d * sizeof(float)>>>(emb, lw, lb, h->adaln, T, d);
+    if (cudaGetLastError() != cudaSuccess) { ldm_destroy(h); return fail(LDM_ERR_CUDA, "adaln_table_kernel launch failed"); }
+  }
+
+  // per-head padded QKV row map: dst row = which*512 + head*64 + j  <-  src row which*d + head*58 + j (j < 58)
+  const int dh = d / desc->n_heads;
+  std::vector<int> qmap(kQkvN);
+  for (int r = 0; r < kQkvN; ++r) {
+    const int which = r / (8 * kHeadPad), hh = (r % (8 * kHeadPad)) / kHeadPad, j = r % kHeadPad;
+    qmap[r] = j < dh ? which * d + hh * dh + j : -1;
+  }
+  int* qmap_dev = nullptr;
+  TRY(dev_upload(h, &qmap_dev, qmap.data(), qmap.size()));
+
+  for (int l = 0; l < L; ++l) {
+    float* tmp = nullptr;
+    TRY(dev_upload(h, &tmp, w->in_proj_w + static_cast<size_t>(l) * 3 * d * d, static_cast<size_t>(3) * d * d));
+    TRY(pack16(h, &h->wqkv[l], tmp, qmap_dev, kQkvN, d, d));
+    std::vector<float> bq(kQkvN, 0.0f);
+    for (int r = 0; r < kQkvN; ++r) if (qmap[r] >= 0) bq[r] = w->in_proj_b[static_cast<size_t>(l) * 3 * d + qmap[r]];
+    TRY(dev_upload(h, &h->bqkv[l], bq.data(), bq.size()));
+    TRY(dev_upload(h, &tmp, w->out_proj_w + static_cast<size_t>(l) * d * d, static_cast<size_t>(d) * d));
+    TRY(pack16(h, &h->wo[l], tmp, nullptr, d, d, d));
+    TRY(dev_upload(h, &h->bo[l], w->out_proj_b + static_cast<size_t>(l) * d, static_cast<size_t>(d)));
+    TRY(dev_upload(h, &tmp, w->linear1_w + static_cast<size_t>(l) * ff * d, static_cast<size_t>(ff) * d));
+    TRY(pack16(h, &h->w1[l], tmp, nullptr, ff, d, d));
+    TRY(dev_upload(h, &h->b1[l], w->linear1_b + static_cast<size_t>(l) * ff, static_cast<size_t>(ff)));
+    TRY(dev_upload(h, &tmp, w->linear2_w + static_cast<size_t>(l) * d * ff, static_cast<size_t>(d) * ff));
+    TRY(pack16(h, &h->w2[l], tmp, nullptr, d, ff, ff));
+    TRY(dev_upload(h, &h->b2[l], w->linear2_b + static_cast<size_t>(l) * d, static_cast<size_t>(d)));
+    TRY(dev_upload(h, &h->ln2w[l], w->norm2_w + static_cast<size_t>(l) * d, static_cast<size_t>(d)));
+    TRY(dev_upload(h, &h->ln2b[l], w->norm2_b + static_cast<size_t>(l) * d, static_cast<size_t>(d)));
+    TRY(make_map(&h->m_wqkv[l], h->wqkv[l], kQkvN, d, 256, h->bf16));
+    TRY(make_map(&h->m_wo[l], h->wo[l], d, d, kD / 2, h->bf16));
+    TRY(make_map(&h->m_w1[l], h->w1[l], ff, d, 240, h->bf16));
+    TRY(make_map(&h->m_w2[l], h->w2[l], d, ff, kD / 2, h->bf16));
+  }
+  {
+    float* tmp = nullptr;
+    TRY(dev_upload(h, &tmp, w->head_w, static_cast<size_t>(C) * d));
+    std::vector<int> hmap(kLogitLd);
+    for (int r = 0; r < kLogitLd; ++r) hmap[r] = r < C ? r : -1;
+    int* hmap_dev = nullptr;
+    TRY(dev_upload(h, &hmap_dev, hmap.data(), hmap.size()));
+    TRY(pack16(h, &h->whead, tmp, hmap_dev, kLogitLd, d, d));
+    TRY(make_map(&h->m_whead, h->whead, kLogitLd, d, kLogitLd, h->bf16));
+  }
+  {
+    std::vector<float> sch(static_cast<size_t>(h->G) * 8 * (T + 1));
+    for (int g = 0; g < h->G; ++g) {
+      const int N = desc->q_type == 0 ? (g == 0 ? desc->n_cat : desc->n_bins) + 1 : C - 1;
+      build_schedule(*desc, N, sch.data() + static_cast<size_t>(g) * 8 * (T + 1));
+    }
+    TRY(dev_upload(h, &h->sched, sch.data(), sch.size()));
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) { ldm_destroy(h); return fail(LDM_ERR_CUDA, "weight packing failed: %s", cudaGetErrorString(cudaGetLastError())); }
+
+  if (h->bf16) {
+    TRY((set_smem(gemm_tc_kernel<256, 256, 4, EPI_QKV, true>, GemmSmem<256, 4>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 4, EPI_RELU, true>, GemmSmem<240, 4>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<160, 160, 4, EPI_F32, true>, GemmSmem<160, 4>::kBytes)));
+    TRY((set_smem(gemm_ln_kernel<true>, kLnSmemBytes)));
+    TRY((set_smem(attention_kernel<true>, kAttSmemBytes)));
+  } else {
+    TRY((set_smem(gemm_tc_kernel<256, 256, 4, EPI_QKV, false>, GemmSmem<256, 4>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 4, EPI_RELU, false>, GemmSmem<240, 4>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<160, 160, 4, EPI_F32, false>, GemmSmem<160, 4>::kBytes)));
+    TRY((set_smem(gemm_ln_kernel<false>, kLnSmemBytes)));
+    TRY((set_smem(attention_kernel<false>, kAttSmemBytes)));
+  }
+#undef TRY
+  *out = h;
+  return LDM_OK;
+}
+
+int ldm_destroy(LdmHandle* h) {
+  if (!h) return LDM_OK;
+  cudaSetDevice(h->desc.device);
+  for (void* p : h->owned) cudaFree(p);
+  void* ws[] = {h->x16, h->qkv16, h->att16, h->z16, h->hid16, h->x32, h->y32, h->logits, h->ids[0], h->ids[1], h->ids_final, h->c_seq, h->c_seq_orig, h->c_mask, h->c_tbl};
+  for (void* p : ws) if (p) cudaFree(p);
+  delete h;
+  return LDM_OK;
+}
+
+int ldm_step(LdmHandle* h, int32_t B, const int64_t* ids_in, int32_t t_model, int32_t t_post, const LdmCond* cond,
+             const LdmSampling* sampling, uint64_t seed, uint32_t step_ctr, int64_t b_global0, int64_t* ids_out,
+             float* logits_out, float* logprob_out, const float* logits_in, const float* logprob_in, void* stream) {
+  int rc = validate_common(h, B, sampling);
+  if (rc) return rc;
+  if (!ids_in || !ids_out) return fail(LDM_ERR_INVALID, "ids_in / ids_out must not be null");
+  CK(cudaSetDevice(h->desc.device));
+  return step_impl(h, B, reinterpret_cast<const long long*>(ids_in), t_model, t_post, cond, sampling, seed, step_ctr, b_global0,
+                   reinterpret_cast<long long*>(ids_out), logits_out, logprob_out, logits_in, logprob_in, static_cast<cudaStream_t>(stream));
+}
+
+int ldm_sample_loop(LdmHandle* h, int32_t B, int32_t n_steps, const int32_t* t_model, const int32_t* t_post, const LdmCond* cond,
+                    const LdmSampling* sampling, uint64_t seed, int64_t b_global0, const int64_t* ids_init, int64_t* ids_out,
+                    int64_t* ids_trace, void* stream) {
+  int rc = validate_common(h, B, sampling);
+  if (rc) return rc;
+  if (n_steps < 1 || !t_model || !t_post || !ids_out) return fail(LDM_ERR_INVALID, "bad loop arguments");
+  for (int i = 0; i < n_steps; ++i) {
+    if (i > 0 && t_model[i] >= t_model[i - 1]) return fail(LDM_ERR_INVALID, "timesteps must be strictly decreasing (base.py:361-362 raises NotImplementedError)");
+  }
+  CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = ensure_workspace(h, B);
+  if (rc) return rc;
+  const size_t nid = static_cast<size_t>(B) * h->S;
+  const long long* cur = nullptr;
+  if (ids_init) cur = reinterpret_cast<const long long*>(ids_init);
+  else if (cond && cond->seq) cur = reinterpret_cast<const long long*>(cond->seq);
+  else {
+    fill_ids_kernel<<<256, 256, 0, st>>>(h->ids[0], static_cast<long long>(h->C - 1), nid);
+    h->launches++;
+    cur = h->ids[0];
+  }
+  for (int i = 0; i < n_steps; ++i) {
+    long long* dst;
+    if (ids_trace) dst = reinterpret_cast<long long*>(ids_trace) + static_cast<size_t>(i) * nid;
+    else if (i == n_steps - 1) dst = reinterpret_cast<long long*>(ids_out);
+    else dst = (cur == h->ids[0]) ? h->ids[1] : h->ids[0];
+    rc = step_impl(h, B, cur, t_model[i], t_post[i], cond, sampling, seed, static_cast<uint32_t>(i), b_global0, dst, nullptr, nullptr, nullptr, nullptr, st);
+    if (rc) return rc;
+    cur = dst;
+  }
+  if (ids_trace) CK(cudaMemcpyAsync(ids_out, cur, nid * 8, cudaMemcpyDeviceToDevice, st));
+  return LDM_OK;
+}
+
+int ldm_sample_host(LdmHandle* h, int32_t B, int32_t n_steps, const int32_t* t_model, const int32_t* t_post,
+                    const int64_t* cond_seq, const uint8_t* cond_mask, const int64_t* cond_seq_orig, const float* refine_table,
+                    int32_t pad_disable, const LdmSampling* sampling, uint64_t seed, int64_t b_global0, const int64_t* ids_init,
+                    int64_t* ids_out, void* stream, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  int rc = validate_common(h, B, sampling);
+  if (rc) return rc;
+  if (!ids_out) return fail(LDM_ERR_INVALID, "ids_out_host must not be null");
+  CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = ensure_workspace(h, B);
+  if (rc) return rc;
+  const size_t nid = static_cast<size_t>(B) * h->S;
+  int64_t up = 0;
+  LdmCond cond{};
+  if (cond_seq) {
+    CK(cudaMemcpyAsync(h->c_seq, cond_seq, nid * 8, cudaMemcpyHostToDevice, st)); up += nid * 8;
+    cond.seq = reinterpret_cast<const int64_t*>(h->c_seq);
+    if (cond_mask) { CK(cudaMemcpyAsync(h->c_mask, cond_mask, nid, cudaMemcpyHostToDevice, st)); up += nid; cond.mask = h->c_mask; }
+    if (cond_seq_orig && refine_table) {
+      CK(cudaMemcpyAsync(h->c_seq_orig, cond_seq_orig, nid * 8, cudaMemcpyHostToDevice, st)); up += nid * 8;
+      cond.seq_orig = reinterpret_cast<const int64_t*>(h->c_seq_orig);
+      const size_t tb = static_cast<size_t>(h->C) * h->C * 4;
+      if (!h->c_tbl) CK(cudaMalloc(reinterpret_cast<void**>(&h->c_tbl), tb));
+      CK(cudaMemcpyAsync(h->c_tbl, refine_table, tb, cudaMemcpyHostToDevice, st)); up += tb;
+      cond.refine_table = h->c_tbl;
+    }
+    cond.pad_disable = pad_disable;
+  }
+  const int64_t* init_dev = nullptr;
+  if (ids_init) {
+    // the start state travels from the host like any other input (x_T); it lands in the second ping-pong buffer
+    CK(cudaMemcpyAsync(h->ids[1], ids_init, nid * 8, cudaMemcpyHostToDevice, st)); up += nid * 8;
+    init_dev = reinterpret_cast<const int64_t*>(h->ids[1]);
+  }
+  rc = ldm_sample_loop(h, B, n_steps, t_model, t_post, cond_seq ? &cond : nullptr, sampling, seed, b_global0, init_dev,
+                       reinterpret_cast<int64_t*>(h->ids_final), nullptr, stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ids_out, h->ids_final, nid * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (h2d_bytes) *h2d_bytes = up;
+  if (d2h_bytes) *d2h_bytes = static_cast<int64_t>(nid * 8);
+  return LDM_OK;
+}
+
+int64_t ldm_launch_count(const LdmHandle* h) { return h ? h->launches : 0; }
+
+int ldm_debug_set_stop_after(LdmHandle* h, int32_t n_launches) {
+  if (!h) return fail(LDM_ERR_INVALID, "null handle");
+  h->debug_stop_after = n_launches;
+  return LDM_OK;
+}
+
+int64_t ldm_debug_read(const LdmHandle* h, const char* name, void* dst, int64_t capacity_bytes, int32_t n_layouts) {
+  if (!h || !name || n_layouts > h->cap) return -1;
+  const size_t M = static_cast<size_t>(n_layouts) * kBM;
+  const int d = h->desc.d_model, ff = h->desc.d_ff;
+  const void* src = nullptr; size_t bytes = 0;
+  if (!strcmp(name, "x32")) { src = h->x32; bytes = M * d * 4; }
+  else if (!strcmp(name, "y32")) { src = h->y32; bytes = M * d * 4; }
+  else if (!strcmp(name, "x16")) { src = h->x16; bytes = M * d * 2; }
+  else if (!strcmp(name, "z16")) { src = h->z16; bytes = M * d * 2; }
+  else if (!strcmp(name, "att16")) { src = h->att16; bytes = M * d * 2; }
+  else if (!strcmp(name, "qkv16")) { src = h->qkv16; bytes = M * kQkvN * 2; }
+  else if (!strcmp(name, "hid16")) { src = h->hid16; bytes = M * ff * 2; }
+  else if (!strcmp(name, "logits")) { src = h->logits; bytes = M * kLogitLd * 4; }
+  else return -1;
+  if (dst && capacity_bytes >= static_cast<int64_t>(bytes)) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+    if (cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  }
+  return static_cast<int64_t>(bytes);
+}
+int32_t ldm_num_classes(const LdmHandle* h) { return h ? h->C : 0; }
+int32_t ldm_seq_len(const LdmHandle* h) { return h ? h->S : 0; }
+
+int64_t ldm_get_schedule(const LdmHandle* h, float* dst, int64_t capacity) {
+  if (!h) return 0;
+  const int64_t n = static_cast<int64_t>(h->G) * 8 * (h->T + 1);
+  if (dst && capacity >= n) cudaMemcpy(dst, h->sched, n * 4, cudaMemcpyDeviceToHost);
+  return n;
+}
+int64_t ldm_get_adaln_table(const LdmHandle* h, float* dst, int64_t capacity) {
+  if (!h) return 0;
+  const int64_t n = static_cast<int64_t>(h->L) * h->T * 2 * h->desc.d_model;
+  if (dst && capacity >= n) cudaMemcpy(dst, h->adaln, n * 4, cudaMemcpyDeviceToHost);
+  return n;
+}
+
+}  // extern "C"

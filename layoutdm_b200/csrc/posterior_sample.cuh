@@ -1,0 +1,261 @@
+// Step epilogue: logits -> log p(x0|xt) -> mask-and-replace posterior -> conditioning adjustments -> categorical draw.
+// One warp per token, no (B,C,S) temporaries.  Replaces, per diffusion step (reference file:line):
+//   predict_start                 T/models/categorical_diffusion/base.py:127-146
+//   q_posterior (constrained)     T/models/categorical_diffusion/constrained.py:135-206 (+ q_pred :112-133, :92-110)
+//   q_posterior (vanilla)         T/models/categorical_diffusion/vanilla.py:112-151
+//   Converter f_to_p_log/p_to_f_log   T/helpers/layout_tokenizer.py:540-557  (here: compile-free vocab group test)
+//   strong mask / refinement / pad-disable   base.py:243-284, T/helpers/task.py:154-224
+//   sample()                      T/helpers/sampling.py:81-130 ; torch.multinomial(p,1) == argmax(p / Exp(1))
+// Class ownership inside a warp: lane l holds classes 4l..4l+3 (one float4 of logits, one Philox block) and class 128+l.
+#pragma once
+#include "common.cuh"
+
+namespace ldm {
+
+enum : int { SAMP_DETERMINISTIC = 0, SAMP_RANDOM = 1, SAMP_TOP_K = 2, SAMP_TOP_P = 3, SAMP_GUMBEL = 4 };
+enum : int { COND_HAS_MASK = 1, COND_PAD_DISABLE = 2, COND_REFINE = 4 };
+constexpr int kMaxAttr = 8;
+
+struct StepParams {
+  int n_layouts, S, C, n_attr, pad_id, mask_id;
+  int constrained;                       // 1: per-attribute groups, 0: vanilla (single group over all classes)
+  int grp_start[kMaxAttr], grp_n[kMaxAttr];
+  int T, t_post;
+  const float* sched;                    // [G][8][T+1]
+  const float* logits; int ld_logits;    // [n_layouts*128][ld]; row = b*128 + s      (nullptr if logprob_in)
+  const float* logprob_in;               // [n_layouts][S][C] or nullptr: draw from given log-probs (relation hook)
+  const long long* ids_in;               // [n_layouts][S]
+  const long long* cond_seq; const unsigned char* cond_mask; const long long* cond_seq_orig; const float* refine_tbl;
+  int cond_flags;
+  int mode; float temperature; float top_p; int top_k;
+  unsigned long long seed; unsigned int step_ctr; long long b_global0;
+  long long* ids_out;                    // [n_layouts][S]
+  float* logprob_out;                    // [n_layouts][S][C] or nullptr
+};
+
+LDM_DEVINL float log_add_exp(float a, float b) {   // util.py:19-21
+  const float m = fmaxf(a, b);
+  return m + logf(expf(a - m) + expf(b - m));
+}
+
+__global__ void __launch_bounds__(256) posterior_sample_kernel(const StepParams p) {
+  const int token = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (token >= p.n_layouts * p.S) return;
+  const int b = token / p.S, s = token % p.S;
+  const int C = p.C;
+  int cls[5]; bool valid[5];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { cls[j] = 4 * lane + j; valid[j] = cls[j] < C; }
+  cls[4] = 128 + lane; valid[4] = cls[4] < C;
+
+  const int x_t = static_cast<int>(p.ids_in[token]);
+  float lp[5];
+
+  if (p.logprob_in != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) lp[j] = valid[j] ? p.logprob_in[static_cast<size_t>(token) * C + cls[j]] : -INFINITY;
+  } else {
+    // ---- predict_start: float64 log-softmax over the C-1 non-MASK classes, clamp [-70, 0] ----
+    const float* lrow = p.logits + (static_cast<size_t>(b) * 128 + s) * p.ld_logits;
+    float l[5];
+    {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(lrow) + lane);
+      l[0] = v.x; l[1] = v.y; l[2] = v.z; l[3] = v.w;
+      l[4] = valid[4] ? __ldg(lrow + cls[4]) : 0.0f;
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) if (valid[j] && cls[j] < C - 1) mx = fmaxf(mx, l[j]);
+    mx = warp_max(mx);
+    double dsum = 0.0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) if (valid[j] && cls[j] < C - 1) dsum += exp(static_cast<double>(l[j]) - static_cast<double>(mx));
+    dsum = warp_sum_d(dsum);
+    const double lse = static_cast<double>(mx) + log(dsum);
+    float lx0[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const float v = (cls[j] < C - 1) ? static_cast<float>(static_cast<double>(l[j]) - lse) : -70.0f;
+      lx0[j] = fminf(fmaxf(v, -70.0f), 0.0f);
+    }
+
+    // ---- posterior q(x_{t-1} | x_t, x0~) in log space ----
+    const int g = p.constrained ? (s % p.n_attr) : 0;
+    const int gst = p.grp_start[g], gn = p.grp_n[g];
+    const float* tab = p.sched + static_cast<size_t>(g) * 8 * (p.T + 1);
+    const int t = p.t_post, tm1 = (t - 1 + (p.T + 1)) % (p.T + 1);
+    const int TT = p.T + 1;
+    const float lat = tab[0 * TT + t], lbt = tab[1 * TT + t], lct = tab[2 * TT + t];
+    const float lcat = tab[3 * TT + t], lcbt = tab[4 * TT + t], lcct = tab[5 * TT + t];
+    const float lcat1 = tab[3 * TT + tm1], lcbt1 = tab[4 * TT + tm1], lcct1 = tab[5 * TT + tm1], l1mcct1 = tab[7 * TT + tm1];
+    const bool is_mask = (x_t == p.mask_id);
+
+    bool in_grp[5]; float q[5], one[5];
+    float qmax = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int c = cls[j];
+      in_grp[j] = valid[j] && (p.constrained ? ((c >= gst && c < gst + gn) || c == p.pad_id || c == p.mask_id) : true);
+      q[j] = -INFINITY; one[j] = 0.0f;
+      if (in_grp[j]) {
+        if (c != p.mask_id) {
+          const float v = (c == x_t) ? 0.0f : kLogEps;
+          const float lq = is_mask ? lcct : log_add_exp(v + lcat, lcbt);
+          one[j] = is_mask ? lct : log_add_exp(v + lat, lbt);
+          q[j] = lx0[j] - lq;
+        } else {
+          q[j] = kLogEps;
+          one[j] = is_mask ? 0.0f : kLogEps;
+        }
+        qmax = fmaxf(qmax, q[j]);
+      }
+    }
+    qmax = warp_max(qmax);
+    float qs = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) if (in_grp[j]) qs += expf(q[j] - qmax);
+    const float L = logf(warp_sum(qs)) + qmax;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      if (in_grp[j]) {
+        const float qn = q[j] - L;
+        const float ev = (cls[j] != p.mask_id) ? log_add_exp(qn + lcat1, lcbt1) : log_add_exp(qn + l1mcct1, lcct1);
+        lp[j] = fminf(fmaxf((ev + one[j]) + L, -70.0f), 0.0f);
+      } else {
+        lp[j] = valid[j] ? kLogEps : -INFINITY;
+      }
+    }
+
+    // ---- conditioning adjustments, in the reference's order ----
+    if (p.cond_flags) {
+      const long long cs = p.cond_seq[token];
+      const bool fixed = (p.cond_flags & COND_HAS_MASK) && p.cond_mask[token];
+      if (fixed) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) if (valid[j]) lp[j] = (cls[j] == cs) ? 0.0f : kLogEps;
+      }
+      if ((p.cond_flags & COND_REFINE) && !fixed) {
+        const float* trow = p.refine_tbl + static_cast<size_t>(p.cond_seq_orig[token]) * C;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) if (valid[j]) lp[j] += __ldg(trow + cls[j]);
+      }
+      if ((p.cond_flags & COND_PAD_DISABLE) && (s % p.n_attr != 0) && cs != p.pad_id) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) if (valid[j] && cls[j] == p.pad_id) lp[j] = kLogEps;
+      }
+    }
+  }
+
+  if (p.logprob_out != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) if (valid[j]) p.logprob_out[static_cast<size_t>(token) * C + cls[j]] = lp[j];
+  }
+
+  // ---- draw ----
+  float score[5];
+  if (p.mode == SAMP_DETERMINISTIC) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) score[j] = valid[j] ? lp[j] : -INFINITY;
+  } else {
+    float lg[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) lg[j] = valid[j] ? lp[j] / p.temperature : -INFINITY;
+
+    const unsigned long long tok = (static_cast<unsigned long long>(p.b_global0) + b) * static_cast<unsigned long long>(p.S) + s;
+    const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
+    const uint32_t tok_lo = static_cast<uint32_t>(tok), tok_hi = static_cast<uint32_t>(tok >> 32);
+    const uint32_t w1 = p.step_ctr & 0xFFFFFFu;
+
+    if (p.mode == SAMP_TOP_K || p.mode == SAMP_TOP_P) {
+      float pr[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      if (p.mode == SAMP_TOP_P) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) m = fmaxf(m, lg[j]);
+        m = warp_max(m);
+        float sm = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { pr[j] = valid[j] ? expf(lg[j] - m) : 0.0f; sm += pr[j]; }
+        sm = warp_sum(sm);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) pr[j] = pr[j] / sm;
+      }
+      int n_before[5] = {0, 0, 0, 0, 0};
+      double cum[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) cum[j] = static_cast<double>(pr[j]);
+      for (int src = 0; src < 32; ++src) {
+#pragma unroll
+        for (int jj = 0; jj < 5; ++jj) {
+          const float v2 = __shfl_sync(0xffffffffu, lg[jj], src);
+          const float p2 = __shfl_sync(0xffffffffu, pr[jj], src);
+          const int c2 = (jj < 4) ? 4 * src + jj : 128 + src;
+          if (c2 < C) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              // rank in a descending sort; ties broken by class index
+              const bool before = (v2 > lg[j]) || (v2 == lg[j] && c2 < cls[j]);
+              if (before) { n_before[j] += (p.mode == SAMP_TOP_P) ? 1 : (v2 > lg[j] ? 1 : 0); cum[j] += static_cast<double>(p2); }
+            }
+          }
+        }
+      }
+      if (p.mode == SAMP_TOP_P) {
+        // sampling.py:100-109: drop every class whose inclusive cumulative mass exceeds top_p, except rank 0
+#pragma unroll
+        for (int j = 0; j < 5; ++j) if (valid[j] && n_before[j] > 0 && static_cast<float>(cum[j]) > p.top_p) lg[j] = -INFINITY;
+      } else {
+        // sampling.py:73-78: threshold = k-th largest value (duplicates counted)
+        float thr = INFINITY;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) if (valid[j] && n_before[j] < p.top_k) thr = fminf(thr, lg[j]);
+        thr = -warp_max(-thr);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) if (valid[j] && lg[j] < thr) lg[j] = -INFINITY;
+      }
+    } else if (p.mode == SAMP_GUMBEL) {
+      const uint4 ga = philox4x32_10(make_uint4(static_cast<uint32_t>(lane), w1 | (1u << 24), tok_lo, tok_hi), key);
+      const uint4 gb = philox4x32_10(make_uint4(32u + (static_cast<uint32_t>(lane) >> 2), w1 | (1u << 24), tok_lo, tok_hi), key);
+      const uint32_t gw[5] = {ga.x, ga.y, ga.z, ga.w, (lane & 3) == 0 ? gb.x : (lane & 3) == 1 ? gb.y : (lane & 3) == 2 ? gb.z : gb.w};
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const float u = u01_from_bits(gw[j]);
+        lg[j] += -logf(-logf(u + 1e-30f) + 1e-30f);           // sampling.py:112-116
+      }
+    }
+
+    // probs = softmax(lg) ; multinomial(probs, 1) = argmax(probs / e), e ~ Exp(1)
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) m = fmaxf(m, lg[j]);
+    m = warp_max(m);
+    float ex[5], sm = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { ex[j] = valid[j] ? expf(lg[j] - m) : 0.0f; sm += ex[j]; }
+    sm = warp_sum(sm);
+    const uint4 ra = philox4x32_10(make_uint4(static_cast<uint32_t>(lane), w1, tok_lo, tok_hi), key);
+    const uint4 rb = philox4x32_10(make_uint4(32u + (static_cast<uint32_t>(lane) >> 2), w1, tok_lo, tok_hi), key);
+    const uint32_t rw[5] = {ra.x, ra.y, ra.z, ra.w, (lane & 3) == 0 ? rb.x : (lane & 3) == 1 ? rb.y : (lane & 3) == 2 ? rb.z : rb.w};
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const float e = -logf(u01_from_bits(rw[j]));
+      score[j] = valid[j] ? (ex[j] / sm) / e : -INFINITY;
+    }
+  }
+
+  // argmax with first-index tie break
+  float best = -INFINITY; int best_c = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    if (valid[j] && (score[j] > best || (score[j] == best && cls[j] < best_c))) { best = score[j]; best_c = cls[j]; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+    if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+  }
+  if (lane == 0) p.ids_out[token] = best_c;
+}
+
+}  // namespace ldm

@@ -1,0 +1,235 @@
+"""Host mirror of the reference's diffusion-core class API, running on the sm_100a library.
+
+  FusedMaskAndReplaceDiffusion   <->  BaseMaskAndReplaceDiffusion (+ Constrained / Vanilla subclasses)
+                                      models/categorical_diffusion/base.py:29-371, constrained.py, vanilla.py
+  LayoutDMB200                   <->  LayoutDM   models/layoutdm.py:26-97
+  patch_reference_model(model)   drop-in: re-routes `model.model.sample` / `_sample_single_step` of a live reference
+                                 LayoutDM instance (so src/trainer's test.py / main.py / demo notebook run unchanged).
+
+Same signatures, argument meaning and exception types as the reference; ids are int64, results come back on the CPU
+exactly where the reference returns CPU tensors.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Any, Dict, List, Optional, Union
+
+import torch
+import torch.nn.functional as F
+
+from .engine import Engine, sampling_struct
+from .vocab import Vocab, decode_ids, linear_centers, refinement_table, timestep_plan
+
+
+def _cfg_get(cfg, key, default=None):
+    if cfg is None:
+        return default
+    if hasattr(cfg, "get"):
+        v = cfg.get(key, default)
+    else:
+        v = getattr(cfg, key, default)
+    return default if v is None else v
+
+
+def index_to_log_onehot(x: torch.Tensor, num_classes: int) -> torch.Tensor:
+    """util.py:34-40 : (B, S) -> (B, C, S)"""
+    assert x.max().item() < num_classes, f"Error: {x.max().item()} >= {num_classes}"
+    return torch.log(F.one_hot(x, num_classes).permute(0, 2, 1).float().clamp(min=1e-30))
+
+
+def duplicate_cond(cond: Dict, batch_size: int) -> Dict:
+    """helpers/task.py:235-248"""
+    if cond["seq"].size(0) == 1 and batch_size > 1:
+        for k in cond:
+            if isinstance(cond[k], torch.Tensor):
+                cond[k] = cond[k].repeat([batch_size] + [1] * (cond[k].dim() - 1))
+    return cond
+
+
+class FusedMaskAndReplaceDiffusion:
+    def __init__(self, engine: Engine, tokenizer=None, bbox_centers=None):
+        self.engine = engine
+        self.vocab: Vocab = engine.vocab
+        self.num_classes = self.vocab.C
+        self.max_token_length = self.vocab.S
+        self.num_timesteps = engine.T
+        self.tokenizer = tokenizer
+        # cluster centres used by the refinement prior (task.py:183-189); linear quantisation by default
+        if bbox_centers is None and tokenizer is not None:
+            bt = tokenizer.bbox_tokenizer
+            bbox_centers = [bt.clustering_models[f"{k}-{self.vocab.n_bins}"].cluster_centers_.reshape(-1) for k in ("x", "y", "w", "h")]
+        self.bbox_centers = bbox_centers if bbox_centers is not None else linear_centers(self.vocab.n_bins)
+        self._step_ctr = 0
+        self._seed = 0
+        self.logit_adjust_fn = None      # optional hook f(t, cond, model_log_prob (B,C,S), sampling_cfg) for cond=relation
+
+    @property
+    def device(self) -> torch.device:
+        return self.engine.device
+
+    # ---- helpers -------------------------------------------------------------------------------------
+    def _prepare_cond(self, cond: Optional[Dict], batch_size: int, sampling_cfg) -> Optional[Dict]:
+        if not cond:
+            return None
+        cond = dict(cond)
+        if cond.get("type") == "refinement" and "refine_table" not in cond:
+            # set_additional_conditions_for_refinement (task.py:204-224) without materialising (B,C,S) weak_logits
+            cond["refine_table"] = refinement_table(self.vocab, self.bbox_centers, _cfg_get(sampling_cfg, "refine_mode", "uniform"),
+                                                    _cfg_get(sampling_cfg, "refine_offset_ratio", 0.1),
+                                                    _cfg_get(sampling_cfg, "refine_lambda", 3.0))
+        cond = duplicate_cond(cond, batch_size)
+        for k in list(cond):
+            if isinstance(cond[k], torch.Tensor):
+                cond[k] = cond[k].to(self.device)                              # base.py:328-330
+        return cond
+
+    @staticmethod
+    def _new_seed() -> int:
+        # the reference draws from torch's global generator, so `set_seed` / torch.manual_seed keeps controlling
+        # reproducibility: derive the Philox key from it
+        return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+    # ---- reference API -------------------------------------------------------------------------------
+    def sample(self, batch_size: Optional[int] = 1, cond: Optional[Dict] = None, sampling_cfg=None,
+               get_intermediate_results: bool = False, seed: Optional[int] = None, b_global0: int = 0, **kwargs
+               ) -> Union[torch.LongTensor, List[torch.LongTensor]]:
+        """base.py:293-371"""
+        T_eval = _cfg_get(sampling_cfg, "num_timesteps", self.num_timesteps)
+        plan = timestep_plan(self.num_timesteps, T_eval, float(_cfg_get(sampling_cfg, "time_difference", 0.0)))
+        cond_d = self._prepare_cond(cond, batch_size, sampling_cfg)
+        if cond_d is not None:
+            assert cond_d["seq"].shape[0] == batch_size
+            assert cond_d["seq"].max().item() < self.num_classes
+        seed = self._new_seed() if seed is None else seed
+        if cond_d is not None and cond_d.get("type") == "relation":
+            return self._sample_stepwise(batch_size, plan, cond_d, sampling_cfg, seed, b_global0, get_intermediate_results)
+        res = self.engine.sample_loop(batch_size, plan, sampling_cfg, cond_d, seed=seed, b_global0=b_global0, trace=get_intermediate_results)
+        if get_intermediate_results:
+            return [r for r in res[1].cpu()]
+        return res.cpu()
+
+    def _sample_stepwise(self, B, plan, cond, sampling_cfg, seed, b_global0, trace):
+        """per-step host loop: needed when a Python hook edits the log-probs between posterior and draw (cond=relation)"""
+        ids = cond["seq"].clone() if cond else torch.full((B, self.max_token_length), self.vocab.mask_id, device=self.device)
+        results = []
+        for i, (t_model, t_post) in enumerate(plan):
+            ids = self._step_ids(ids, t_model, t_post, sampling_cfg, cond, seed, i, b_global0)
+            if trace:
+                results.append(ids.cpu())
+        return results if trace else ids.cpu()
+
+    def _step_ids(self, ids, t_model, t_post, sampling_cfg, cond, seed, step_ctr, b_global0=0):
+        if cond is not None and cond.get("type") == "relation" and self.logit_adjust_fn is not None:
+            _, _, lp = self.engine.step(ids, t_model, t_post, sampling_cfg, cond, seed, step_ctr, b_global0, want_logprob=True)
+            lp = self.logit_adjust_fn(t_model, cond, lp.permute(0, 2, 1).contiguous(), sampling_cfg)      # (B,C,S) like the reference
+            # pad-disable is applied after `update` in the reference (base.py:261-284)
+            lp = lp.permute(0, 2, 1).contiguous()
+            S = ids.shape[1]
+            pad_mask = (torch.arange(S, device=ids.device)[None] % self.vocab.n_attr != 0) & (cond["seq"] != self.vocab.pad_id)
+            lp[..., self.vocab.pad_id] = torch.where(pad_mask, torch.full_like(lp[..., 0], -69.07755278982137), lp[..., self.vocab.pad_id])
+            out, _, _ = self.engine.step(ids, t_model, t_post, sampling_cfg, cond, seed, step_ctr, b_global0, logprob_in=lp)
+            return out
+        out, _, _ = self.engine.step(ids, t_model, t_post, sampling_cfg, cond, seed, step_ctr, b_global0)
+        return out
+
+    def _sample_single_step(self, log_z: torch.Tensor, model_t: torch.Tensor, skip_step: int, sampling_cfg=None,
+                            cond: Optional[Dict] = None) -> torch.Tensor:
+        """base.py:205-291 ; log_z (B,C,S) -> log_z (B,C,S).  Kept for API compatibility (the notebook and subclasses call it);
+        `sample()` itself never materialises (B,C,S) tensors."""
+        ids = log_z.argmax(1).to(self.device)
+        t_model = int(model_t[0].item())
+        assert bool((model_t == t_model).all())
+        td = float(_cfg_get(sampling_cfg, "time_difference", 0.0))
+        T = self.num_timesteps
+        noise_t = min(max(t_model - int(T * td), 0), T - 1) if td > 0.0 else t_model            # :218-225
+        t_post = noise_t - skip_step if (skip_step > 0 and noise_t > skip_step) else noise_t   # :227-240
+        cond_d = None
+        if cond:
+            cond_d = {k: (v.to(self.device) if isinstance(v, torch.Tensor) else v) for k, v in cond.items()}
+            if cond_d.get("type") == "refinement" and "refine_table" not in cond_d:
+                cond_d = self._prepare_cond(cond_d, ids.shape[0], sampling_cfg)
+        out = self._step_ids(ids, t_model, t_post, sampling_cfg, cond_d, self._seed, self._step_ctr)
+        self._step_ctr += 1
+        return index_to_log_onehot(out, self.num_classes)
+
+    def reset_noise(self, seed: int):
+        self._seed, self._step_ctr = seed, 0
+
+    def predict_logits(self, ids: torch.Tensor, t: int) -> torch.Tensor:
+        """CategoricalTransformer.forward (nn_lib.py:191-237): ids (B,S) -> logits (B,S,C) on the GPU"""
+        s = sampling_struct({"name": "deterministic"})
+        _, lg, _ = self.engine.step(ids.to(self.device), t, t, s, want_logits=True)
+        return lg
+
+
+class LayoutDMB200:
+    """LayoutDM wrapper (models/layoutdm.py:26-97): `.sample()` returns decoded layouts on the CPU."""
+
+    def __init__(self, engine: Engine, tokenizer=None, bbox_centers=None):
+        self.model = FusedMaskAndReplaceDiffusion(engine, tokenizer, bbox_centers)
+        self.tokenizer = tokenizer
+        self.vocab = engine.vocab
+        self._centers = bbox_centers
+
+    @classmethod
+    def from_state_dict(cls, sd, dataset: str = "rico25", num_timesteps: int = 100, q_type: str = "constrained",
+                        operand_dtype: str = "fp16", device=None, tokenizer=None, bbox_centers=None) -> "LayoutDMB200":
+        vocab = Vocab.from_tokenizer(tokenizer) if tokenizer is not None else Vocab.for_dataset(dataset)
+        eng = Engine.from_state_dict(sd, vocab, num_timesteps=num_timesteps, q_type=q_type, operand_dtype=operand_dtype, device=device)
+        return cls(eng, tokenizer, bbox_centers)
+
+    def eval(self):
+        return self
+
+    def sample(self, batch_size: Optional[int] = 1, cond: Optional[Dict] = None, sampling_cfg=None, **kwargs) -> Dict[str, torch.Tensor]:
+        """layoutdm.py:77-88 (extra kwargs such as cond_type= / device= are swallowed like the reference does)"""
+        kw = {k: v for k, v in kwargs.items() if k in ("seed", "b_global0", "get_intermediate_results")}
+        ids = self.model.sample(batch_size=batch_size, cond=cond, sampling_cfg=sampling_cfg, **kw)
+        if self.tokenizer is not None:
+            return self.tokenizer.decode(ids)
+        return decode_ids(ids, self.vocab, self._centers)
+
+    def aggregate_sampling_settings(self, sampling_cfg, args):
+        """base_model.py:124-150 + layoutdm.py:90-97"""
+        if args.cond == "refinement" and args.refine_lambda > 0.0:
+            sampling_cfg.refine_mode = args.refine_mode
+            sampling_cfg.refine_offset_ratio = args.refine_offset_ratio
+            sampling_cfg.refine_lambda = args.refine_lambda
+        if args.cond == "relation" and args.relation_lambda > 0.0:
+            sampling_cfg.relation_mode = args.relation_mode
+            sampling_cfg.relation_lambda = args.relation_lambda
+            sampling_cfg.relation_tau = args.relation_tau
+            sampling_cfg.relation_num_update = args.relation_num_update
+        if "num_timesteps" not in sampling_cfg:
+            sampling_cfg.num_timesteps = args.num_timesteps
+        if args.time_difference > 0:
+            sampling_cfg.time_difference = args.time_difference
+        return sampling_cfg
+
+
+def patch_reference_model(model, operand_dtype: str = "fp16", device=None):
+    """Drop-in for a live reference `trainer.models.layoutdm.LayoutDM`: after `load_state_dict`, call
+    `patch_reference_model(model)`; `model.sample(...)` (layoutdm.py:77) and `model.model.sample(...)` /
+    `_sample_single_step(...)` then run on the sm_100a library.  Training `forward` is untouched."""
+    core = model.model.module if hasattr(model.model, "module") else model.model
+    tok = model.tokenizer
+    vocab = Vocab.from_tokenizer(tok)
+    q_type = "vanilla" if type(core).__name__.startswith("Vanilla") else "constrained"
+    eng = Engine.from_state_dict(model.state_dict(), vocab, num_timesteps=core.num_timesteps, q_type=q_type,
+                                 operand_dtype=operand_dtype, device=device)
+    fused = FusedMaskAndReplaceDiffusion(eng, tok)
+    if q_type == "constrained" or True:
+        try:
+            from trainer.models.categorical_diffusion.logit_adjustment import update as _update
+
+            def _hook(t, cond, model_log_prob, sampling_cfg):
+                if "batch_w_canvas" not in cond:
+                    return model_log_prob
+                return _update(t=t, cond=cond, model_log_prob=model_log_prob, tokenizer=tok, sampling_cfg=sampling_cfg)
+            fused.logit_adjust_fn = _hook
+        except Exception:       # reference not importable: relation conditioning falls back to plain sampling
+            pass
+    core.sample = fused.sample
+    core._sample_single_step = fused._sample_single_step
+    core._ldm_b200 = fused
+    return model

@@ -213,39 +213,45 @@ def adaln_table(sd, spec: ModelSpec, layer: int) -> torch.Tensor:
 
 def denoiser_forward(sd, ids: torch.Tensor, t: int, vocab: VocabSpec, spec: ModelSpec,
                      operand_dtype: Optional[torch.dtype] = None,
-                     return_hidden: bool = False) -> torch.Tensor:
+                     taps: Optional[dict] = None) -> torch.Tensor:
     """ids (B,S) int64, scalar timestep t -> logits (B,S,C) fp32.
 
     With operand_dtype = torch.float16 / bfloat16 every GEMM operand (activations AND weights, and the
     attention probabilities) is rounded to that dtype first while accumulation stays fp32: this is the
-    'same-rounding' oracle for the tensor-core path.  operand_dtype=None is the exact fp32 restatement."""
+    'same-rounding' oracle for the tensor-core path.  operand_dtype=None is the exact fp32 restatement.
+    taps: optional dict that receives the intermediate tensors of every layer (for kernel-by-kernel tests)."""
     d, H, dh = spec.d, spec.heads, spec.dh
     B, S = ids.shape
     r = lambda x: _rnd(x, operand_dtype)
+    tap = (lambda k, v: taps.__setitem__(k, v)) if taps is not None else (lambda k, v: None)
     h = sd[PREFIX + "cat_emb.weight"][ids] + positional_table(sd, vocab, spec)[None]   # nn_lib.py:204,220 (dropout = id in eval)
-    hidden = []
     for l in range(spec.layers):
         p = f"{PREFIX}backbone.layers.{l}."
         emb = adaln_table(sd, spec, l)[t]                       # (2d,)
         scale, shift = emb[:d], emb[d:]                         # torch.chunk(emb, 2)  transformer_utils.py:81
         x = F.layer_norm(h, (d,), eps=1e-5) * (1 + scale) + shift   # :82
+        tap(f"x{l}", x)
         # MHA(x,x,x): torch.nn.MultiheadAttention, batch_first, no masks (transformer_utils.py:140-142,197-204)
         qkv = F.linear(r(x), r(sd[p + "self_attn.in_proj_weight"]), sd[p + "self_attn.in_proj_bias"])
         q, k, v = qkv.split(d, dim=-1)
         q = q.view(B, S, H, dh).transpose(1, 2) * (1.0 / math.sqrt(dh))
         k = k.view(B, S, H, dh).transpose(1, 2)
         v = v.view(B, S, H, dh).transpose(1, 2)
+        tap(f"q{l}", q); tap(f"k{l}", k); tap(f"v{l}", v)       # (B,H,S,dh); q already scaled
         att = torch.softmax(r(q) @ r(k).transpose(-1, -2), dim=-1)
         o = (r(att) @ r(v)).transpose(1, 2).reshape(B, S, d)
+        tap(f"att{l}", o)
         x = x + F.linear(r(o), r(sd[p + "self_attn.out_proj.weight"]), sd[p + "self_attn.out_proj.bias"])  # residual from the NORMALISED x (:175-178)
+        tap(f"y{l}", x)
         z = F.layer_norm(x, (d,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], eps=1e-5)
+        tap(f"z{l}", z)
         f = F.relu(F.linear(r(z), r(sd[p + "linear1.weight"]), sd[p + "linear1.bias"]))
+        tap(f"hid{l}", f)
         h = x + F.linear(r(f), r(sd[p + "linear2.weight"]), sd[p + "linear2.bias"])                    # :179
-        hidden.append(h)
+        tap(f"h{l}", h)
     hn = F.layer_norm(h, (d,), sd[PREFIX + "head.0.weight"], sd[PREFIX + "head.0.bias"], eps=1e-5)
+    tap("hn", hn)
     logits = F.linear(r(hn), r(sd[PREFIX + "head.1.weight"]))                                          # nn_lib.py:187-189,235
-    if return_hidden:
-        return logits, hidden
     return logits
 
 

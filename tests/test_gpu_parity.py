@@ -1,0 +1,229 @@
+"""GPU (-m gpu): the CUDA path against the golden fixtures recorded from the reference and against the oracle.
+Everything goes through the C ABI (layoutdm_b200.Engine is a thin ctypes wrapper)."""
+import numpy as np
+import pytest
+import torch
+
+from fixtures import NAMES, Fixture
+from oracle import layoutdm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL_SAME_ROUNDING = 1e-3     # north-star gate: max-abs on fp32 logits vs the oracle with the same operand rounding
+LOGIT_TOL_FP32 = {"fp16": 6e-3, "bf16": 6e-2}   # reported deviation vs the true fp32 reference (weights x2-x3 the init scale)
+
+_engines = {}
+
+
+def engine_for(fx, dtype="fp16"):
+    from layoutdm_b200 import Engine, Vocab
+    key = (fx.meta["dataset"], fx.meta["T"], fx.meta["q_type"], fx.meta["weight_scale"], dtype)
+    if key not in _engines:
+        _engines.clear()
+        torch.cuda.empty_cache()
+        _engines[key] = Engine.from_state_dict(fx.weights(), Vocab.for_dataset(fx.meta["dataset"]), num_timesteps=fx.meta["T"],
+                                               q_type=fx.meta["q_type"], operand_dtype=dtype)
+    return _engines[key]
+
+
+def cond_cuda(fx):
+    if fx.cond is None:
+        return None
+    return {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in fx.cond.items()}
+
+
+def test_schedule_and_adaln_tables():
+    fx = Fixture("rico25_uncond_random")
+    eng = engine_for(fx)
+    sch, osch = eng.schedule_tables(), O.group_schedules(fx.spec.T, fx.vocab)
+    for g in range(5):
+        for r, name in enumerate(O.SCHED_NAMES):
+            a, b = sch[g, r, : osch[g][name].shape[0]], osch[g][name]
+            fin = torch.isfinite(b)
+            assert torch.equal(torch.isfinite(a), fin)
+            assert (a[fin] - b[fin]).abs().max() <= 1e-6 * b[fin].abs().max().clamp(min=1.0)
+    ad = eng.adaln_table()
+    oad = torch.stack([O.adaln_table(fx.weights(), fx.spec, l) for l in range(fx.spec.layers)])
+    assert (ad - oad).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_step_epilogue_is_id_exact_on_reference_logits(name):
+    """posterior + cond adjustments + draw, fed with the REFERENCE's fp32 logits under the shared-noise contract:
+    token ids must be bit-exact, log-probs within 1e-4."""
+    fx = Fixture(name)
+    eng = engine_for(fx)
+    cond = cond_cuda(fx)
+    for i in fx.trace_steps:
+        t_model, t_post = fx.plan[i]
+        out, _, lp = eng.step(fx.x_in[i].cuda(), t_model, t_post, fx.cfg_dict, cond, seed=fx.meta["noise_seed"], step_ctr=i,
+                              want_logprob=True, logits_in=fx.logits(i).cuda())
+        torch.cuda.synchronize()
+        assert (lp.cpu() - fx.logp(i)).abs().max() < 1e-4
+        assert torch.equal(out.cpu(), fx.x_out[i]), f"{name} step {i}: {(out.cpu() != fx.x_out[i]).sum().item()} ids differ"
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_epilogue_every_step_against_oracle(name):
+    """same check on every loop iteration (all timesteps, skip steps, time_difference), logits from the fp32 oracle"""
+    fx = Fixture(name)
+    eng = engine_for(fx)
+    cond = cond_cuda(fx)
+    orc = O.Oracle(fx.vocab, fx.spec, fx.weights(), q_type=fx.meta["q_type"])
+    n = len(fx.plan)
+    g = torch.Generator().manual_seed(0)
+    bad = 0
+    for i in sorted(set(range(0, n, max(1, n // 12))) | {n - 1}):
+        t_model, t_post = fx.plan[i]
+        logits = torch.randn(fx.B, fx.vocab.S, fx.vocab.C, generator=g) * 3.0
+        lp_o = orc.logprob_from_logits(logits, fx.x_in[i], t_post, fx.cond)
+        u, ug = fx.noise(i)
+        want = O.draw(lp_o, fx.cfg, u, ug)
+        out, _, lp = eng.step(fx.x_in[i].cuda(), t_model, t_post, fx.cfg_dict, cond, seed=fx.meta["noise_seed"], step_ctr=i,
+                              want_logprob=True, logits_in=logits.cuda())
+        assert (lp.cpu() - lp_o).abs().max() < 1e-4
+        bad += int((out.cpu() != want).sum())
+    assert bad == 0
+
+
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+@pytest.mark.parametrize("name", ["rico25_uncond_random", "publaynet_c_top_p", "rico25_refinement_T200"])
+def test_denoiser_logits(name, dtype):
+    """tcgen05 denoiser: <= 1e-3 max-abs vs the same-rounding oracle (fp16 operands; bf16 gets its own, looser bound),
+    and the deviation from the reference's true-fp32 logits stays within the documented envelope."""
+    fx = Fixture(name)
+    eng = engine_for(fx, dtype)
+    odt = torch.float16 if dtype == "fp16" else torch.bfloat16
+    for i in fx.trace_steps:
+        t_model, t_post = fx.plan[i]
+        _, lg, _ = eng.step(fx.x_in[i].cuda(), t_model, t_post, {"name": "deterministic"}, want_logits=True)
+        lg = lg.cpu()
+        assert torch.isfinite(lg).all()
+        with torch.no_grad():
+            same = O.denoiser_forward(fx.weights(), fx.x_in[i], t_model, fx.vocab, fx.spec, operand_dtype=odt)
+        d_same = (lg - same).abs().max().item()
+        d_ref = (lg - fx.logits(i)).abs().max().item()
+        print(f"{name} step {i} {dtype}: |logits - same-rounding oracle| = {d_same:.2e}, |logits - fp32 reference| = {d_ref:.2e}")
+        assert d_same < (LOGIT_TOL_SAME_ROUNDING if dtype == "fp16" else 8e-3)
+        assert d_ref < LOGIT_TOL_FP32[dtype]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_full_step_ids_vs_reference(name):
+    """whole step (denoiser + epilogue) on the reference's own x_t: ids equal the reference's except where the 16-bit
+    operand rounding moves a near-tie; fixed tokens are always exact."""
+    fx = Fixture(name)
+    eng = engine_for(fx)
+    cond = cond_cuda(fx)
+    n = len(fx.plan)
+    steps = sorted(set(range(0, n, max(1, n // 10))) | {n - 1})
+    mism = tot = 0
+    for i in steps:
+        t_model, t_post = fx.plan[i]
+        out, _, _ = eng.step(fx.x_in[i].cuda(), t_model, t_post, fx.cfg_dict, cond, seed=fx.meta["noise_seed"], step_ctr=i)
+        out = out.cpu()
+        mism += int((out != fx.x_out[i]).sum()); tot += out.numel()
+        if fx.cond is not None:
+            m = fx.cond["mask"]
+            assert torch.equal(out[m], fx.cond["seq"][m])
+    print(f"{name}: {mism}/{tot} ids differ from the fp32 reference")
+    assert mism / tot < 0.01
+
+
+def test_loop_equals_stepwise_and_host_entry():
+    fx = Fixture("publaynet_c_top_p")
+    eng = engine_for(fx)
+    cond = cond_cuda(fx)
+    plan = fx.plan[:12]
+    ids, trace = eng.sample_loop(fx.B, plan, fx.cfg_dict, cond, seed=5, trace=True)
+    x = fx.cond["seq"].cuda()
+    for i, (tm, tp) in enumerate(plan):
+        x, _, _ = eng.step(x, tm, tp, fx.cfg_dict, cond, seed=5, step_ctr=i)
+        assert torch.equal(x, trace[i])
+    assert torch.equal(ids, trace[-1])
+    ids2 = eng.sample_loop(fx.B, plan, fx.cfg_dict, cond, seed=5)
+    assert torch.equal(ids2, ids)
+    host_cond = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in fx.cond.items()}
+    ids3, h2d, d2h = eng.sample_host(fx.B, plan, fx.cfg_dict, host_cond, seed=5)
+    assert torch.equal(ids3, ids.cpu()) and d2h == fx.B * 125 * 8 and h2d >= fx.B * 125 * 9
+
+
+def test_noise_is_keyed_by_global_layout_index():
+    """shard invariance: layouts [4,8) of a B=8 call == a B=4 call with b_global0=4"""
+    fx = Fixture("rico25_uncond_random")
+    eng = engine_for(fx)
+    plan = fx.plan[-6:]
+    cfg = {"name": "random", "temperature": 1.0}
+    init = torch.randint(0, fx.vocab.C, (8, 125), generator=torch.Generator().manual_seed(1)).cuda()
+    full = eng.sample_loop(8, plan, cfg, seed=9, ids_init=init)
+    part = eng.sample_loop(4, plan, cfg, seed=9, ids_init=init[4:], b_global0=4)
+    assert torch.equal(full[4:], part)
+    other = eng.sample_loop(4, plan, cfg, seed=10, ids_init=init[4:], b_global0=4)
+    assert not torch.equal(other, part)
+
+
+@pytest.mark.parametrize("B", [1, 5, 148, 1024])
+def test_invariants_at_scale(B):
+    """size-independent properties at the BASELINE batch sizes: ids in range, no MASK after t=0, fixed tokens kept,
+    no PAD in bbox slots of real elements (cond=c)."""
+    fx = Fixture("publaynet_c_top_p")
+    eng = engine_for(fx)
+    v = fx.vocab
+    g = torch.Generator().manual_seed(B)
+    n_el = torch.randint(1, 26, (B,), generator=g)
+    seq = torch.full((B, 125), v.mask_id, dtype=torch.long)
+    mask = torch.zeros(B, 125, dtype=torch.bool)
+    for b in range(B):
+        n = int(n_el[b])
+        seq[b, 0:5 * n:5] = torch.randint(0, v.n_cat, (n,), generator=g)
+        mask[b, 0:5 * n:5] = True
+        seq[b, 5 * n:] = v.pad_id
+        mask[b, 5 * n:] = True
+    cond = dict(seq=seq.cuda(), mask=mask.cuda(), type="c")
+    plan = [fx.plan[i] for i in (0, 30, 60, 90, 99)]
+    ids = eng.sample_loop(B, plan, fx.cfg_dict, cond, seed=3).cpu()
+    assert ids.min() >= 0 and ids.max() < v.C
+    assert (ids != v.mask_id).all()
+    assert torch.equal(ids[mask], seq[mask])
+    real = (torch.arange(125)[None] % 5 != 0) & (seq != v.pad_id)
+    assert (ids[real] != v.pad_id).all()
+    # every generated attribute token lies in its own attribute's vocabulary slice
+    for a in range(1, 5):
+        tok = ids[:, a::5][real[:, a::5]]
+        lo = v.n_cat + (a - 1) * v.n_bins
+        assert ((tok >= lo) & (tok < lo + v.n_bins)).all()
+
+
+def test_error_behaviour_mirrors_reference():
+    fx = Fixture("rico25_uncond_random")
+    eng = engine_for(fx)
+    x = torch.full((2, 125), fx.vocab.mask_id, dtype=torch.long).cuda()
+    with pytest.raises(AssertionError):          # constrained.py:139
+        eng.step(x, 100, 100, {"name": "random"})
+    with pytest.raises(AssertionError):          # util.py:35
+        eng.step(torch.full_like(x, 155), 5, 5, {"name": "random"})
+    with pytest.raises(NotImplementedError):     # base.py:361-362
+        eng.sample_loop(2, [(5, 5), (5, 5)], {"name": "random"})
+    with pytest.raises(NotImplementedError):     # sampling.py:117-118
+        eng.step(x, 5, 5, {"name": "nucleus"})
+
+
+def test_class_api_mirror():
+    """FusedMaskAndReplaceDiffusion / LayoutDMB200 keep the reference signatures (sample, _sample_single_step, decode)"""
+    from layoutdm_b200 import LayoutDMB200
+    fx = Fixture("rico25_uncond_T50")
+    model = LayoutDMB200.from_state_dict(fx.weights(), dataset="rico25", num_timesteps=100)
+    torch.manual_seed(0)
+    out = model.sample(batch_size=3, cond=None, sampling_cfg={"name": "random", "temperature": 1.0, "num_timesteps": 10}, cond_type="unconditional")
+    assert out["bbox"].shape == (3, 25, 4) and out["label"].shape == (3, 25) and out["mask"].dtype == torch.bool and not out["bbox"].is_cuda
+    torch.manual_seed(0)
+    out2 = model.sample(batch_size=3, sampling_cfg={"name": "random", "temperature": 1.0, "num_timesteps": 10})
+    assert torch.equal(out["bbox"], out2["bbox"])       # torch.manual_seed controls the noise like in the reference
+    core = model.model
+    res = core.sample(batch_size=2, sampling_cfg={"name": "random", "temperature": 1.0, "num_timesteps": 5}, get_intermediate_results=True)
+    assert isinstance(res, list) and len(res) == 5 and res[0].shape == (2, 125) and res[0].dtype == torch.int64
+    log_z = torch.log(torch.nn.functional.one_hot(torch.full((2, 125), 154), 155).permute(0, 2, 1).float().clamp(min=1e-30)).cuda()
+    nxt = core._sample_single_step(log_z, torch.full((2,), 98, device="cuda"), 1, {"name": "random", "temperature": 1.0}, None)
+    assert nxt.shape == (2, 155, 125)
+    with pytest.raises(AssertionError):      # base.py:311
+        core.sample(batch_size=1, sampling_cfg={"name": "random", "num_timesteps": 101})

@@ -1,0 +1,111 @@
+"""CPU: host-side mirror logic and the C-ABI surface (no compute calls -- there is no GPU here)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import layoutdm_b200 as L
+from layoutdm_b200 import _lib
+from layoutdm_b200.engine import Engine, sampling_struct
+from oracle import layoutdm_oracle as O
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_package_does_not_import_oracle():
+    for f in os.listdir(os.path.join(REPO, "layoutdm_b200")):
+        if f.endswith(".py"):
+            src = open(os.path.join(REPO, "layoutdm_b200", f)).read()
+            assert "oracle" not in src.replace("# oracle", ""), f"{f} must not reference the oracle"
+
+
+@pytest.mark.parametrize("T,T_eval,td", [(100, 100, 0.0), (100, 50, 0.0), (100, 30, 0.05), (200, 200, 0.0), (100, 7, 0.2), (100, 1, 0.0)])
+def test_timestep_plan_matches_oracle(T, T_eval, td):
+    assert L.timestep_plan(T, T_eval, td) == O.timestep_plan(T, T_eval, td)
+
+
+def test_timestep_plan_rejects_too_many_steps():
+    with pytest.raises(AssertionError):
+        L.timestep_plan(100, 101)
+
+
+def test_decode_and_refinement_table_match_oracle():
+    for vo, vl in ((O.RICO25, L.Vocab.for_dataset("rico25")), (O.PUBLAYNET, L.Vocab.for_dataset("publaynet"))):
+        assert (vo.C, vo.S, vo.pad_id, vo.mask_id) == (vl.C, vl.S, vl.pad_id, vl.mask_id)
+        g = torch.Generator().manual_seed(0)
+        ids = torch.randint(0, vo.C, (16, vo.S), generator=g)
+        a, b = O.decode_ids(ids, vo), L.decode_ids(ids, vl)
+        for k in a:
+            assert torch.equal(a[k], b[k])
+        for mode in ("uniform", "gaussian", "negative"):
+            ta = O.refinement_table(vo, O.linear_centers(), mode, 0.1, 3.0)
+            tb = L.refinement_table(vl, L.linear_centers(), mode, 0.1, 3.0)
+            assert torch.equal(ta, tb)
+        # decode with explicit centres == linear decode when the centres are the linear ones
+        c = L.decode_ids(ids, vl, L.linear_centers())
+        assert torch.allclose(c["bbox"], b["bbox"], atol=1e-6)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    hdr = open(os.path.join(REPO, "include", "ldm_b200.h")).read()
+    declared = set(re.findall(r"\b(ldm_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert b"sm_100a" in lib.ldm_version()
+
+
+def test_struct_layout_matches_header(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "ldm_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(LdmModelDesc), sizeof(LdmWeights), sizeof(LdmCond), sizeof(LdmSampling));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [ctypes.sizeof(_lib.LdmModelDesc), ctypes.sizeof(_lib.LdmWeights), ctypes.sizeof(_lib.LdmCond), ctypes.sizeof(_lib.LdmSampling)]
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    sd = O.make_weights(O.RICO25, O.ModelSpec(layers=1), seed=0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine.from_state_dict(sd, L.Vocab.for_dataset("rico25"))
+
+
+def test_pack_state_dict_shapes_and_prefixes():
+    spec = O.ModelSpec()
+    sd = O.make_weights(O.RICO25, spec, seed=0)
+    v = L.Vocab.for_dataset("rico25")
+    w = Engine.pack_state_dict(sd, v)
+    assert w["in_proj_w"].shape == (4, 3 * 464, 464) and w["pos_table"].shape == (125, 464) and w["head_w"].shape == (155, 464)
+    assert torch.equal(w["pos_table"], O.positional_table(sd, O.RICO25, spec))
+    # other prefixes a user may hand in (un-wrapped module, bare transformer)
+    for new in ("model.transformer.", "transformer.", ""):
+        sd2 = {k.replace("model.module.transformer.", new): t for k, t in sd.items()}
+        w2 = Engine.pack_state_dict(sd2, v)
+        assert torch.equal(w2["linear2_w"], w["linear2_w"])
+    with pytest.raises(KeyError):
+        Engine.pack_state_dict({"foo": torch.zeros(1)}, v)
+    # vanilla-config positional embedding (nn_lib.py:73-88)
+    sd3 = O.make_weights(O.RICO25, O.ModelSpec(pos_emb="default"), seed=0)
+    w3 = Engine.pack_state_dict(sd3, v)
+    assert torch.equal(w3["pos_table"], sd3[O.PREFIX + "pos_emb.pos_emb"])
+
+
+def test_sampling_struct_mirrors_reference_errors():
+    s = sampling_struct({"name": "top_p", "top_p": 0.9, "temperature": 1.0})
+    assert (s.mode, round(s.top_p, 3)) == (3, 0.9)
+    with pytest.raises(NotImplementedError):
+        sampling_struct({"name": "top_k_top_p"})      # sampling.py:117-118
+    with pytest.raises(AssertionError):
+        sampling_struct({"name": "top_p", "top_p": 1.5})   # sampling.py:96
+
+    class Cfg:   # attribute-style config (OmegaConf DictConfig behaves like both)
+        name, temperature = "random", 0.7
+    assert abs(sampling_struct(Cfg()).temperature - 0.7) < 1e-6
