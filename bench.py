@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- layouts/sec of the LayoutDM denoising loop (BASELINE.json metric) on N GPUs of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one full pass of the hot path over one batch: `sample()` of B=1024 layouts per GPU through all T=100
+denoising iterations (BASELINE.json configs[1]: rico25 unconditional, T=100, batch 1024, random sampling).
+Prints ONE JSON line (rank 0).  `value` = layouts/s with everything device-resident; `e2e` = the same metric through
+the host-buffer C-ABI entry (ldm_sample_host: pinned-host inputs -> H2D -> loop -> D2H of the ids);
+`roofline` = the dominant kernel against the measured bf16 tensor peak; `cpu_baseline` = the oracle port of the
+reference's CPU path on a bounded sample.  `--impl reference` times that CPU path alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "layouts_per_sec_T100_batch1024_N25"
+UNIT = "layouts/s"
+T = 100
+# algorithmic FLOPs per layout per launch (unpadded shapes, SURVEY.md 8d / BASELINE.md 3)
+FLOPS = {"qkv_gemm": 161_472_000, "outproj_ln_gemm": 53_824_000, "ff1_gemm": 215_296_000, "ff2_ln_gemm": 215_296_000,
+         "attention": 29_000_000, "head_gemm": 17_980_000}
+FLOPS_PER_LAYOUT_STEP = 2_717_532_000
+
+
+def load_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(burst=d["bf16_tflops"], sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), hbm=d["hbm_gbs"], src="measured (MEASURED_PEAKS.json)")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        # under load = samples at or above the median of the upper half
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", local) if torch.cuda.is_available() else None)
+    return world, rank, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def max_over_ranks(x: float, world, device):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores (oracle port; the reference itself is Python and lives in
+# /root/reference, which does not exist on the GPU box)
+# --------------------------------------------------------------------------------------------------------------
+def cpu_pass(orc, O, B, timesteps, seed):
+    """runs `len(timesteps)` of the T denoising iterations for B layouts; returns seconds"""
+    vo = orc.vocab
+    x = torch.full((B, vo.S), vo.mask_id, dtype=torch.long)
+    cfg = O.SamplingCfg(name="random")
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for i, t in enumerate(timesteps):
+            lp, _ = orc.step_logprob(x, t, t)
+            x = O.draw(lp, cfg, O.uniforms(seed, i, 0, 0, B, vo.S, vo.C))
+    return time.perf_counter() - t0
+
+
+def make_cpu_oracle():
+    from oracle import layoutdm_oracle as O          # allowed here: cpu_baseline / --impl reference legs only
+    from layoutdm_b200 import Vocab
+    from layoutdm_b200.synthetic import random_state_dict
+    sd = random_state_dict(Vocab.for_dataset("rico25"), num_timesteps=T, seed=0)
+    return O.Oracle(O.RICO25, O.ModelSpec(T=T), sd), O
+
+
+def cpu_sample_plan(budget_s, orc, O):
+    """pick (B_s, n_t) so that one bounded sample costs about budget_s seconds"""
+    B_s = 64
+    t1 = cpu_pass(orc, O, B_s, [50], 0)               # calibration (also warms the thread pool)
+    t1 = min(t1, cpu_pass(orc, O, B_s, [50], 0))
+    n_t = int(max(1, min(T, budget_s / max(t1, 1e-3))))
+    return B_s, n_t, t1
+
+
+def run_reference_arm(args, world, rank):
+    if rank != 0:
+        return
+    orc, O = make_cpu_oracle()
+    cores = torch.get_num_threads()
+    total_budget = 150.0
+    per = max(2.0, min(20.0, total_budget / (args.steps + args.warmup)))
+    B_s, n_t, t1 = cpu_sample_plan(per, orc, O)
+    ts = [int(round(i * (T - 1) / max(1, n_t - 1))) for i in range(n_t)][::-1] if n_t > 1 else [50]
+    for _ in range(args.warmup):
+        cpu_pass(orc, O, B_s, ts, 1)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        cpu_pass(orc, O, B_s, ts, 2 + k)
+    dt = (time.perf_counter() - t0) / args.steps
+    lps = B_s / (dt * T / len(ts))                    # layouts per second for the full T-step loop
+    sample = f"{B_s} layouts x {len(ts)} of {T} timesteps per step (fp32 torch-CPU port of the reference path), extrapolated x{T / len(ts):.1f} to T={T}"
+    line = {"impl": "reference", "metric": METRIC, "value": lps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "rico25 unconditional, T=100, random sampling, N=25 (S=125, C=155); CPU sample of the batch-1024 workload"},
+            "cpu_baseline": {"value": lps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": lps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+def run_b200_arm(args, world, rank, local):
+    from layoutdm_b200 import Engine, Vocab, timestep_plan
+    from layoutdm_b200.parallel import all_gather_ids
+    from layoutdm_b200.synthetic import random_state_dict
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    vocab = Vocab.for_dataset("rico25")
+    eng = Engine.from_state_dict(random_state_dict(vocab, num_timesteps=T, seed=0), vocab, num_timesteps=T, operand_dtype=args.dtype, device=local)
+    B = args.batch                                    # per GPU (weak scaling: configs[4] = 8 x 1024)
+    total = B * world
+    plan = timestep_plan(T, T)
+    cfg = {"name": "random", "temperature": 1.0}
+    b0 = rank * B
+
+    def device_pass(seed):
+        ids = eng.sample_loop(B, plan, cfg, seed=seed, b_global0=b0)
+        return all_gather_ids(ids, total) if world > 1 else ids
+
+    for w in range(max(args.warmup, 3)):
+        device_pass(100 + w)
+    torch.cuda.synchronize()
+    barrier(world)
+
+    # ---- device-resident timing (CUDA events on the launching stream) ----
+    l0 = eng.launch_count
+    with ClockSampler(local) as cs:
+        torch.cuda.synchronize(); barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(args.steps):
+            out = device_pass(1000 + k)
+        e1.record()
+        torch.cuda.synchronize(); barrier(world)
+        ms_total = e0.elapsed_time(e1)
+    launches = eng.launch_count - l0
+    ms_total = max_over_ranks(ms_total, world, dev)
+    ms_step = ms_total / args.steps
+    value = total / (ms_step * 1e-3)
+    clocks = cs.summary()
+    assert int(out.max()) < vocab.mask_id, "MASK token survived the loop"
+
+    # ---- end to end through the host-buffer entry (pinned host buffers, H2D + D2H inside the timed region) ----
+    init = torch.full((B, vocab.S), vocab.mask_id, dtype=torch.int64).pin_memory()
+    host_out = torch.empty(B, vocab.S, dtype=torch.int64).pin_memory()
+    eng.sample_host(B, plan, cfg, seed=7, b_global0=b0, ids_init=init, out=host_out)
+    torch.cuda.synchronize(); barrier(world)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        _, h2d, d2h = eng.sample_host(B, plan, cfg, seed=2000 + k, b_global0=b0, ids_init=init, out=host_out)
+    torch.cuda.synchronize(); barrier(world)
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps, world, dev)
+    e2e = {"value": total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d + 2 * 4 * len(plan)), "d2h_bytes_per_step": int(d2h),
+           "path": "ldm_sample_host (pinned host ids_init -> H2D, 100-step loop, D2H of final ids); per-rank shard, max over ranks"}
+
+    # ---- per-kernel timing for the roofline (one extra profiled pass; CUDA events around every launch) ----
+    eng.profile_begin()
+    eng.sample_loop(B, plan, cfg, seed=5, b_global0=b0)
+    prof = eng.profile_end()
+    peaks = load_peaks()
+    gemm = {k: v for k, v in prof.items() if k in FLOPS and v[1] > 0}
+    dom = max(gemm, key=lambda k: gemm[k][0])
+    dom_ms, dom_n = gemm[dom]
+    achieved = FLOPS[dom] * B / (dom_ms / dom_n * 1e-3) / 1e12
+    tot_prof = sum(v[0] for v in prof.values())
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["sustained"], "traffic": None, "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
+                "share_of_step": dom_ms / tot_prof,
+                "kernels": {k: {"ms_per_pass": round(v[0], 3), "launches": v[1], "share": round(v[0] / tot_prof, 4),
+                                **({"tflops": round(FLOPS[k] * B / (v[0] / v[1] * 1e-3) / 1e12, 1)} if k in FLOPS and v[1] else {})}
+                            for k, v in prof.items() if v[1]},
+                "path_tflops": value / world * T * FLOPS_PER_LAYOUT_STEP / 1e12,
+                "path_frac": value / world * T * FLOPS_PER_LAYOUT_STEP / 1e12 / peaks["sustained"]}
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        orc, O = make_cpu_oracle()
+        B_s, n_t, _ = cpu_sample_plan(15.0, orc, O)
+        ts = [int(round(i * (T - 1) / max(1, n_t - 1))) for i in range(n_t)][::-1] if n_t > 1 else [50]
+        dt = cpu_pass(orc, O, B_s, ts, 3)
+        cpu = {"value": B_s / (dt * T / len(ts)), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{B_s} layouts x {len(ts)} of {T} timesteps ({dt:.1f} s of CPU work), extrapolated to T={T}; fp32 torch-CPU port of the reference path"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": "rico25 unconditional, T=100, batch=1024 per GPU, N=25 (S=125 tokens, C=155), sampling=random, random-init weights",
+                           "global_batch": total, "parallelism": f"dp{world} (batch-sharded replicas, one all-gather of ids)" if world > 1 else "single GPU",
+                           "l2": "per-step activation working set (1.9 GB at B=1024) >> 126 MB L2, no explicit flush needed",
+                           "operands": f"{args.dtype} tensor-core operands, fp32 accumulate / LayerNorm / softmax / posterior"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+        run_reference_arm(args, world, rank)
+        return
+    world, rank, local = dist_setup(args.gpus)
+    try:
+        run_b200_arm(args, world, rank, local)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -9,6 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libldm_b200.so")
 
 LDM_OK, LDM_ERR_INVALID, LDM_ERR_CUDA, LDM_ERR_UNSUPPORTED = 0, -1, -2, -3
+PROFILE_CATEGORIES = ("embed_adaln", "qkv_gemm", "attention", "outproj_ln_gemm", "ff1_gemm", "ff2_ln_gemm", "head_gemm", "posterior_sample", "misc")
 SAMPLING_MODES = {"deterministic": 0, "random": 1, "top_k": 2, "top_p": 3, "gumbel": 4}
 
 
@@ -51,6 +52,8 @@ SIGNATURES = {
     "ldm_seq_len": (C.c_int32, [C.c_void_p]),
     "ldm_get_schedule": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
     "ldm_get_adaln_table": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "ldm_profile_begin": (C.c_int, [C.c_void_p]),
+    "ldm_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64), C.c_int32]),
     "ldm_debug_set_stop_after": (C.c_int, [C.c_void_p, C.c_int32]),
     "ldm_debug_read": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]),
     "ldm_last_error": (C.c_char_p, []),

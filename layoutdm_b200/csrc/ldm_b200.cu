@@ -96,6 +96,9 @@ struct LdmHandle {
   int num_sms = 148;
   int64_t launches = 0;
   int debug_stop_after = 0;   // test tap: stop the denoiser after this many launches (0 = run everything)
+  bool prof = false;          // per-kernel CUDA-event timing (ldm_profile_begin/end)
+  struct ProfRec { int cat; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
   // parameters (device)
   float *cat_emb = nullptr, *pos = nullptr, *adaln = nullptr, *sched = nullptr;
   void *wqkv[kMaxLayers] = {}, *wo[kMaxLayers] = {}, *w1[kMaxLayers] = {}, *w2[kMaxLayers] = {}, *whead = nullptr;
@@ -169,6 +172,21 @@ void build_schedule(const LdmModelDesc& d, int N, float* out /*[8][T+1]*/) {
   }
 }
 
+enum : int { CAT_EMBED = 0, CAT_QKV, CAT_ATTN, CAT_OUTPROJ, CAT_FF1, CAT_FF2, CAT_HEAD, CAT_EPILOGUE, CAT_MISC, CAT_COUNT };
+
+struct ProfScope {   // counts the launch; when profiling is on, brackets it with a CUDA-event pair on the launching stream
+  LdmHandle* h; cudaStream_t st; cudaEvent_t b = nullptr;
+  ProfScope(LdmHandle* h_, int cat, cudaStream_t st_) : h(h_), st(st_) {
+    h->launches++;
+    if (h->prof) {
+      cudaEvent_t a; cudaEventCreate(&a); cudaEventCreate(&b);
+      cudaEventRecord(a, st);
+      h->prof_recs.push_back({cat, a, b});
+    }
+  }
+  ~ProfScope() { if (b) cudaEventRecord(b, st); }
+};
+
 template <typename K>
 int set_smem(K kernel, int bytes) {
   CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -212,37 +230,40 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
   const int d = h->desc.d_model, ff = h->desc.d_ff, L = h->L, T = h->T;
   const int M = n * kBM;
   const int sms = h->num_sms;
+  int done = 0;
+  // test tap: stop after `debug_stop_after` launches
+#define LDM_STAGE_DONE() do { if (h->debug_stop_after && ++done >= h->debug_stop_after) { CK(cudaGetLastError()); return LDM_OK; } } while (0)
   {
     const int warps = n * 128, blocks = (warps * 32 + 255) / 256;
+    ProfScope ps(h, CAT_EMBED, st);
     embed_adaln_kernel<BF16><<<blocks, 256, 0, st>>>(ids_in, h->cat_emb, h->pos, h->adaln + (static_cast<size_t>(0) * T + t_model) * 2 * d,
                                                      h->x32, h->x16, n, h->S, d);
-    h->launches++;
   }
-  int done = 1;
-#define LDM_STAGE_DONE() do { if (h->debug_stop_after && ++done > h->debug_stop_after) { CK(cudaGetLastError()); return LDM_OK; } } while (0)
-  if (h->debug_stop_after == 1) { CK(cudaGetLastError()); return LDM_OK; }
+  LDM_STAGE_DONE();
   for (int l = 0; l < L; ++l) {
     {  // QKV projection (+bias, q * 1/sqrt(head_dim))
       GemmParams p{M, kQkvN, d, kQkvN / 256, h->bqkv[l], h->qkv16, kQkvN, 1.0f / sqrtf(static_cast<float>(d / h->desc.n_heads)), 8 * kHeadPad};
       const int tiles = n * p.n_tiles;
+      ProfScope ps(h, CAT_QKV, st);
       gemm_tc_kernel<256, 256, 4, EPI_QKV, BF16><<<std::min(tiles, sms), kGemmThreads, GemmSmem<256, 4>::kBytes, st>>>(h->m_x16, h->m_wqkv[l], p);
-      h->launches++;
     }
     LDM_STAGE_DONE();
-    attention_kernel<BF16><<<n * h->desc.n_heads, kAttThreads, kAttSmemBytes, st>>>(h->qkv16, h->att16, h->S, d / h->desc.n_heads, h->desc.n_heads);
-    h->launches++;
+    {
+      ProfScope ps(h, CAT_ATTN, st);
+      attention_kernel<BF16><<<n * h->desc.n_heads, kAttThreads, kAttSmemBytes, st>>>(h->qkv16, h->att16, h->S, d / h->desc.n_heads, h->desc.n_heads);
+    }
     LDM_STAGE_DONE();
     {  // out-projection + residual (normalised x) + LayerNorm2
       GemmLnParams p{M, d, h->bo[l], h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr, h->z16};
+      ProfScope ps(h, CAT_OUTPROJ, st);
       gemm_ln_kernel<BF16><<<std::min(n, sms), kGemmThreads, kLnSmemBytes, st>>>(h->m_att16, h->m_wo[l], p);
-      h->launches++;
     }
     LDM_STAGE_DONE();
     {  // FF1 + ReLU
       GemmParams p{M, ff, d, ff / kFF1Tile, h->b1[l], h->hid16, ff, 1.0f, 0};
       const int tiles = n * p.n_tiles;
+      ProfScope ps(h, CAT_FF1, st);
       gemm_tc_kernel<kFF1Tile, 240, 4, EPI_RELU, BF16><<<std::min(tiles, sms), kGemmThreads, GemmSmem<240, 4>::kBytes, st>>>(h->m_z16, h->m_w1[l], p);
-      h->launches++;
     }
     LDM_STAGE_DONE();
     {  // FF2 + residual + (next block's AdaLN | head LayerNorm)
@@ -254,16 +275,17 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       } else {
         p.ln_scale = h->hlnw; p.ln_shift = h->hlnb; p.adaln = 0; p.out32 = nullptr; p.out16 = h->z16;
       }
+      ProfScope ps(h, CAT_FF2, st);
       gemm_ln_kernel<BF16><<<std::min(n, sms), kGemmThreads, kLnSmemBytes, st>>>(h->m_hid16, h->m_w2[l], p);
-      h->launches++;
     }
     LDM_STAGE_DONE();
   }
   {  // vocabulary head -> fp32 logits
     GemmParams p{M, kLogitLd, d, 1, nullptr, h->logits, kLogitLd, 1.0f, 0};
+    ProfScope ps(h, CAT_HEAD, st);
     gemm_tc_kernel<160, 160, 4, EPI_F32, BF16><<<std::min(n, sms), kGemmThreads, GemmSmem<160, 4>::kBytes, st>>>(h->m_z16, h->m_whead, p);
-    h->launches++;
   }
+#undef LDM_STAGE_DONE
   CK(cudaGetLastError());
   return LDM_OK;
 }
@@ -288,15 +310,15 @@ int step_impl(LdmHandle* h, int B, const long long* ids_in, int t_model, int t_p
   if (rc) return rc;
   if (logprob_in == nullptr) {
     if (logits_in != nullptr) {
+      ProfScope ps(h, CAT_MISC, st);
       logits_scatter_kernel<<<1024, 256, 0, st>>>(logits_in, h->logits, B, h->S, h->C);
-      h->launches++;
     } else {
       rc = h->bf16 ? launch_denoiser<true>(h, B, ids_in, t_model, st) : launch_denoiser<false>(h, B, ids_in, t_model, st);
       if (rc) return rc;
     }
     if (logits_out != nullptr) {
+      ProfScope ps(h, CAT_MISC, st);
       logits_gather_kernel<<<1024, 256, 0, st>>>(h->logits, logits_out, B, h->S, h->C);
-      h->launches++;
     }
   }
   StepParams p{};
@@ -319,8 +341,10 @@ int step_impl(LdmHandle* h, int B, const long long* ids_in, int t_model, int t_p
   p.seed = seed; p.step_ctr = step_ctr; p.b_global0 = b_global0;
   p.ids_out = ids_out; p.logprob_out = logprob_out;
   const int warps = B * h->S, blocks = (warps * 32 + 255) / 256;
-  posterior_sample_kernel<<<blocks, 256, 0, st>>>(p);
-  h->launches++;
+  {
+    ProfScope ps(h, CAT_EPILOGUE, st);
+    posterior_sample_kernel<<<blocks, 256, 0, st>>>(p);
+  }
   CK(cudaGetLastError());
   return LDM_OK;
 }
@@ -482,8 +506,8 @@ int ldm_sample_loop(LdmHandle* h, int32_t B, int32_t n_steps, const int32_t* t_m
   if (ids_init) cur = reinterpret_cast<const long long*>(ids_init);
   else if (cond && cond->seq) cur = reinterpret_cast<const long long*>(cond->seq);
   else {
+    ProfScope ps(h, CAT_MISC, st);
     fill_ids_kernel<<<256, 256, 0, st>>>(h->ids[0], static_cast<long long>(h->C - 1), nid);
-    h->launches++;
     cur = h->ids[0];
   }
   for (int i = 0; i < n_steps; ++i) {
@@ -544,6 +568,27 @@ int ldm_sample_host(LdmHandle* h, int32_t B, int32_t n_steps, const int32_t* t_m
 }
 
 int64_t ldm_launch_count(const LdmHandle* h) { return h ? h->launches : 0; }
+
+int ldm_profile_begin(LdmHandle* h) {
+  if (!h) return fail(LDM_ERR_INVALID, "null handle");
+  h->prof = true;
+  return LDM_OK;
+}
+
+int ldm_profile_end(LdmHandle* h, float* ms_per_category, int64_t* launches_per_category, int32_t n_categories) {
+  if (!h) return fail(LDM_ERR_INVALID, "null handle");
+  h->prof = false;
+  CK(cudaDeviceSynchronize());
+  for (int i = 0; i < n_categories; ++i) { if (ms_per_category) ms_per_category[i] = 0.0f; if (launches_per_category) launches_per_category[i] = 0; }
+  for (auto& r : h->prof_recs) {
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    if (r.cat < n_categories) { if (ms_per_category) ms_per_category[r.cat] += ms; if (launches_per_category) launches_per_category[r.cat]++; }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  h->prof_recs.clear();
+  return LDM_OK;
+}
 
 int ldm_debug_set_stop_after(LdmHandle* h, int32_t n_launches) {
   if (!h) return fail(LDM_ERR_INVALID, "null handle");

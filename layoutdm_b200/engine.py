@@ -110,6 +110,16 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.ldm_launch_count(self._h))
 
+    def profile_begin(self):
+        _lib.check(self.lib.ldm_profile_begin(self._h))
+
+    def profile_end(self) -> Dict[str, Tuple[float, int]]:
+        """{category: (total ms, launches)} of everything launched since profile_begin()"""
+        n = len(_lib.PROFILE_CATEGORIES)
+        ms, cnt = (C.c_float * n)(), (C.c_int64 * n)()
+        _lib.check(self.lib.ldm_profile_end(self._h, ms, cnt, n))
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(_lib.PROFILE_CATEGORIES)}
+
     def schedule_tables(self) -> torch.Tensor:
         n = self.lib.ldm_get_schedule(self._h, None, 0)
         out = torch.empty(n, dtype=torch.float32)

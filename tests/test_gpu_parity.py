@@ -9,8 +9,10 @@ from oracle import layoutdm_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_TOL_SAME_ROUNDING = 1e-3     # north-star gate: max-abs on fp32 logits vs the oracle with the same operand rounding
-LOGIT_TOL_FP32 = {"fp16": 6e-3, "bf16": 6e-2}   # reported deviation vs the true fp32 reference (weights x2-x3 the init scale)
+LOGIT_TOL = 1e-3     # north-star gate: max-abs on the fp32 logits vs the reference's fp32 logits, at the reference's own
+                     # weight scale (base_model.py:108-116, std 0.02).  For the x2 / x3 "peaked" stress weights of the
+                     # fixtures the same gate is applied relative to the logit scale: 1e-3 * max|logit|.
+BF16_FACTOR = 10.0   # bf16 operands (the north star's nominal dtype) carry 8x coarser mantissas; measured ~8x the fp16 error
 
 _engines = {}
 
@@ -86,11 +88,34 @@ def test_epilogue_every_step_against_oracle(name):
     assert bad == 0
 
 
+def test_denoiser_logits_at_reference_weight_scale():
+    """the 1e-3 gate proper: tcgen05 denoiser (fp16 operands, fp32 accumulate) vs the fp32 restatement of the reference,
+    weights at the reference's init scale, several timesteps and token mixes"""
+    from layoutdm_b200 import Engine, Vocab
+    vo, spec = O.RICO25, O.ModelSpec()
+    sd = O.make_weights(vo, spec, seed=0, scale=1.0)
+    _engines.clear()
+    eng = Engine.from_state_dict(sd, Vocab.for_dataset("rico25"), num_timesteps=spec.T)
+    g = torch.Generator().manual_seed(0)
+    worst = 0.0
+    for t in (0, 42, 99):
+        ids = torch.randint(0, vo.C, (6, vo.S), generator=g)
+        ids[0] = vo.mask_id
+        ids[1, 60:] = vo.pad_id
+        _, lg, _ = eng.step(ids.cuda(), t, t, {"name": "deterministic"}, want_logits=True)
+        with torch.no_grad():
+            ref = O.denoiser_forward(sd, ids, t, vo, spec)
+        d = (lg.cpu() - ref).abs().max().item()
+        print(f"t={t}: max|logit|={ref.abs().max():.3f} max-abs error {d:.2e}")
+        worst = max(worst, d)
+    assert worst < LOGIT_TOL
+
+
 @pytest.mark.parametrize("dtype", ["fp16", "bf16"])
 @pytest.mark.parametrize("name", ["rico25_uncond_random", "publaynet_c_top_p", "rico25_refinement_T200"])
 def test_denoiser_logits(name, dtype):
-    """tcgen05 denoiser: <= 1e-3 max-abs vs the same-rounding oracle (fp16 operands; bf16 gets its own, looser bound),
-    and the deviation from the reference's true-fp32 logits stays within the documented envelope."""
+    """against the REFERENCE's recorded fp32 logits (stress weights x2..x3): error <= 1e-3 relative to the logit scale for
+    fp16 operands; bf16 within its documented factor.  Also reports the distance to the same-rounding oracle."""
     fx = Fixture(name)
     eng = engine_for(fx, dtype)
     odt = torch.float16 if dtype == "fp16" else torch.bfloat16
@@ -101,11 +126,13 @@ def test_denoiser_logits(name, dtype):
         assert torch.isfinite(lg).all()
         with torch.no_grad():
             same = O.denoiser_forward(fx.weights(), fx.x_in[i], t_model, fx.vocab, fx.spec, operand_dtype=odt)
+        ref = fx.logits(i)
+        scale = max(1.0, ref.abs().max().item())
         d_same = (lg - same).abs().max().item()
-        d_ref = (lg - fx.logits(i)).abs().max().item()
-        print(f"{name} step {i} {dtype}: |logits - same-rounding oracle| = {d_same:.2e}, |logits - fp32 reference| = {d_ref:.2e}")
-        assert d_same < (LOGIT_TOL_SAME_ROUNDING if dtype == "fp16" else 8e-3)
-        assert d_ref < LOGIT_TOL_FP32[dtype]
+        d_ref = (lg - ref).abs().max().item()
+        print(f"{name} step {i} {dtype}: max|logit|={scale:.2f} |d| vs fp32 reference {d_ref:.2e} (rel {d_ref / scale:.2e}), vs same-rounding oracle {d_same:.2e}")
+        tol = LOGIT_TOL * scale * (BF16_FACTOR if dtype == "bf16" else 1.0)
+        assert d_ref < tol and d_same < tol
 
 
 @pytest.mark.parametrize("name", NAMES)
