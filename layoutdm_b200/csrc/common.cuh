@@ -181,12 +181,21 @@ LDM_DEVINL void tmem_st16(uint32_t taddr, const uint32_t (&r)[32]) {
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+LDM_DEVINL void tmem_st8(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
 template <int N>
 LDM_DEVINL void tmem_st(uint32_t taddr, const uint32_t (&r)[32]) {
-  static_assert(N == 16 || N == 32, "unsupported tcgen05.st width");
+  static_assert(N == 8 || N == 16 || N == 32, "unsupported tcgen05.st width");
   if constexpr (N == 32) tmem_st32(taddr, r);
-  else tmem_st16(taddr, r);
+  else if constexpr (N == 16) tmem_st16(taddr, r);
+  else tmem_st8(taddr, r);
 }
+// named barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
+LDM_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------------------
 // operand dtype helpers (fp16 or bf16 tensor-core operands; accumulation is always fp32)

@@ -3,16 +3,18 @@
 //   A : activations, row-major [M][K] 16-bit (fp16 or bf16), M = 128 * n_layouts (one M-tile = one layout)
 //   W : nn.Linear weight, row-major [N][K] 16-bit  (both operands are "K-major" for the MMA)
 //
-// Warp-specialised persistent kernels, 192 threads:
+// Warp-specialised persistent kernels, 320 threads:
 //   warp 0     : TMA producer  (cp.async.bulk.tensor 2-D tiles, 128-byte swizzle, mbarrier complete_tx)
 //   warp 1     : TMEM allocation + single-thread tcgen05.mma issue (fp32 accumulators in TMEM)
-//   warps 2..5 : epilogue; warp w owns TMEM lanes 32*(w%4)..+31, thread = one output row
+//   warps 2..9 : epilogue; warp w owns TMEM lanes 32*(w%4)..+31 (thread = one output row) and one half of the
+//                tile's columns (two warps per scheduler, so one warp's TMEM/global latency hides behind the other)
 //
 // Two kernels:
 //   gemm_tc_kernel : N tiled (UMMA_N <= 256), double-buffered accumulators, epilogues
 //                    QKV (bias, q-scale) / FF1 (bias, ReLU) / head (fp32 logits)
 //   gemm_ln_kernel : the whole d_model = 464 row in one CTA (two MMAs 240 + 224 per k-step), epilogue
-//                    bias + residual + LayerNorm (affine or timestep-adaptive) -- thread-local row statistics.
+//                    bias + residual + LayerNorm (affine or timestep-adaptive): two passes over the TMEM accumulator,
+//                    per-thread row statistics combined across the two column halves through shared memory.
 //
 // Reference ops replaced: nn.Linear / nn.MultiheadAttention projections / nn.LayerNorm / AdaLayerNorm in
 // T/models/transformer_utils.py:79-83,165-210 and T/models/common/nn_lib.py:187-189,235.
@@ -24,7 +26,8 @@ namespace ldm {
 constexpr int kBM = 128;       // rows per M tile (= one layout: 125 tokens + 3 pad rows)
 constexpr int kBK = 64;        // K elements per smem stage (= 128 B = one swizzle row)
 constexpr int kUmmaK = 16;     // K per tcgen05.mma (16-bit operands)
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;
+constexpr int kEpiThreads = 256;   // warps 2..9
 constexpr int kATileBytes = kBM * kBK * 2;   // 16 KB
 
 enum : int { EPI_QKV = 0, EPI_RELU = 1, EPI_F32 = 2 };
@@ -44,7 +47,8 @@ struct GemmSmem {
   static constexpr int kBTileBytes = UMMA_N * kBK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static_assert(kBTileBytes % 1024 == 0, "B tile must keep 1024-B (swizzle atom) alignment");
-  static constexpr int kBytes = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kBiasBytes = 1856 * 4;   // the whole bias vector of the layer lives in smem
+  static constexpr int kBytes = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
 };
 
 template <int BN_STORE, int UMMA_N, int STAGES, int EPI, bool BF16>
@@ -64,16 +68,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* sbias = reinterpret_cast<float*>(smem + STAGES * SM::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + kBK - 1) / kBK;
   const int total_tiles = (p.M / kBM) * p.n_tiles;
+  for (int i = threadIdx.x; i < p.N; i += kGemmThreads) sbias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.0f;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiThreads); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
@@ -127,12 +133,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     // ===================== epilogue warps =====================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;          // which half of the tile's columns
     const int row_in_tile = quad * 32 + lane;
+    constexpr int kFull = BN_STORE / 32, kRem = BN_STORE % 32;
+    constexpr int kSplit = (kFull + 1) / 2;    // half 0: chunks [0, kSplit), half 1: [kSplit, kFull) + remainder
+    static_assert(kRem == 0 || kRem == 8 || kRem == 16, "unsupported tile width");
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
       const int n0 = n_blk * BN_STORE;
       const size_t row = static_cast<size_t>(m_blk) * kBM + row_in_tile;
+      float tile_scale = 1.0f;
+      if constexpr (EPI == EPI_QKV) tile_scale = (n0 < p.qcols) ? p.qscale : 1.0f;   // Q tiles are whole tiles (512 % 256 == 0)
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride;
@@ -141,13 +153,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         constexpr int W = decltype(width_tag)::value;
         uint32_t r[32];
         tmem_ld<W>(taddr + c0, r);
+        float bv[W];
+#pragma unroll
+        for (int j = 0; j < W / 4; ++j) {      // smem broadcast reads overlap the TMEM load
+          const float4 b4 = *reinterpret_cast<const float4*>(sbias + n0 + c0 + 4 * j);
+          bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
+        }
         tmem_wait_ld();
         float v[W];
 #pragma unroll
         for (int j = 0; j < W; ++j) {
-          float x = __uint_as_float(r[j]);
-          if (p.bias != nullptr) x += __ldg(p.bias + n0 + c0 + j);
-          if constexpr (EPI == EPI_QKV) { if (n0 + c0 + j < p.qcols) x *= p.qscale; }
+          float x = __uint_as_float(r[j]) + bv[j];
+          if constexpr (EPI == EPI_QKV) x *= tile_scale;
           if constexpr (EPI == EPI_RELU) x = fmaxf(x, 0.0f);
           v[j] = x;
         }
@@ -164,12 +181,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 O::pack(v[8 * j + 4], v[8 * j + 5]), O::pack(v[8 * j + 6], v[8 * j + 7]));
         }
       };
-      constexpr int kFull = BN_STORE / 32, kRem = BN_STORE % 32;
+      if (half == 0) {
 #pragma unroll 1
-      for (int c = 0; c < kFull; ++c) do_chunk(std::integral_constant<int, 32>{}, c * 32);
-      if constexpr (kRem == 16) do_chunk(std::integral_constant<int, 16>{}, kFull * 32);
-      if constexpr (kRem == 8) do_chunk(std::integral_constant<int, 8>{}, kFull * 32);
-      static_assert(kRem == 0 || kRem == 8 || kRem == 16, "unsupported tile width");
+        for (int c = 0; c < kSplit; ++c) do_chunk(std::integral_constant<int, 32>{}, c * 32);
+      } else {
+#pragma unroll 1
+        for (int c = kSplit; c < kFull; ++c) do_chunk(std::integral_constant<int, 32>{}, c * 32);
+        if constexpr (kRem == 16) do_chunk(std::integral_constant<int, 16>{}, kFull * 32);
+        if constexpr (kRem == 8) do_chunk(std::integral_constant<int, 8>{}, kFull * 32);
+      }
 
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
@@ -190,7 +210,8 @@ constexpr int kLnN1 = 240, kLnN2 = 224;     // the two MMA widths covering 464 c
 constexpr int kLnStages = 3;
 constexpr int kLnBTileBytes = kD * kBK * 2;               // 59392 = 58 * 1024
 constexpr int kLnStageBytes = kATileBytes + kLnBTileBytes; // 75776
-constexpr int kLnSmemBytes = kLnStages * kLnStageBytes + 1024 + 256;
+constexpr int kLnStatBytes = 2 * kBM * 8;          // per-row (sum, sumsq) partials of the two column halves
+constexpr int kLnSmemBytes = kLnStages * kLnStageBytes + 1024 + 256 + kLnStatBytes;
 
 struct GemmLnParams {
   int M, K;
@@ -217,6 +238,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tfull = bars + 2 * kLnStages;
   uint64_t* tempty = tfull + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 1);
+  float2* sstat = reinterpret_cast<float2*>(smem + kLnStages * kLnStageBytes + 256);   // [2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + kBK - 1) / kBK;
@@ -227,7 +249,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tma_prefetch_desc(&map_b);
     for (int i = 0; i < kLnStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(tfull, 1);
-    mbar_init(tempty, 128);
+    mbar_init(tempty, kEpiThreads);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
@@ -279,88 +301,95 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
+    // ===================== epilogue: 8 warps = 4 lane quadrants x 2 column halves of 232 =====================
     using O = OpT<BF16>;
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row_in_tile = quad * 32 + lane;
+    constexpr int kHalfCols = kD / 2;                 // 232 = 7 * 32 + 8
+    const int col0 = half * kHalfCols;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const size_t row = static_cast<size_t>(tile) * kBM + row_in_tile;
       mbar_wait(tfull, acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-      const float* rrow = p.resid + row * kD;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + col0;
+      const float* rrow = p.resid + row * kD + col0;
 
-      // pass 1: y = acc + bias + resid ; keep y in TMEM ; row sum
-      float sum = 0.0f;
+      // pass 1: y = acc + bias + resid ; y back to TMEM (and to y_out) ; partial row sum / sum of squares
+      float sum = 0.0f, sq = 0.0f;
       auto pass1 = [&](auto width_tag, int c0) {
         constexpr int W = decltype(width_tag)::value;
         uint32_t r[32];
         tmem_ld<W>(taddr + c0, r);
+        float4 rs[W / 4], bs[W / 4];
+#pragma unroll
+        for (int j = 0; j < W / 4; ++j) {
+          rs[j] = __ldg(reinterpret_cast<const float4*>(rrow + c0) + j);
+          bs[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0) + j);
+        }
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < W / 4; ++j) {
-          const float4 rs = __ldg(reinterpret_cast<const float4*>(rrow + c0) + j);
-          const float4 bs = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j);
           float4 y;
-          y.x = __uint_as_float(r[4 * j + 0]) + bs.x + rs.x;
-          y.y = __uint_as_float(r[4 * j + 1]) + bs.y + rs.y;
-          y.z = __uint_as_float(r[4 * j + 2]) + bs.z + rs.z;
-          y.w = __uint_as_float(r[4 * j + 3]) + bs.w + rs.w;
+          y.x = __uint_as_float(r[4 * j + 0]) + bs[j].x + rs[j].x;
+          y.y = __uint_as_float(r[4 * j + 1]) + bs[j].y + rs[j].y;
+          y.z = __uint_as_float(r[4 * j + 2]) + bs[j].z + rs[j].z;
+          y.w = __uint_as_float(r[4 * j + 3]) + bs[j].w + rs[j].w;
           sum += (y.x + y.y) + (y.z + y.w);
+          sq = fmaf(y.x, y.x, fmaf(y.y, y.y, fmaf(y.z, y.z, fmaf(y.w, y.w, sq))));
           r[4 * j + 0] = __float_as_uint(y.x); r[4 * j + 1] = __float_as_uint(y.y);
           r[4 * j + 2] = __float_as_uint(y.z); r[4 * j + 3] = __float_as_uint(y.w);
-          if (p.y_out != nullptr) reinterpret_cast<float4*>(p.y_out + row * kD + c0)[j] = y;
+          if (p.y_out != nullptr) reinterpret_cast<float4*>(p.y_out + row * kD + col0 + c0)[j] = y;
         }
         tmem_st<W>(taddr + c0, r);
       };
 #pragma unroll 1
-      for (int c = 0; c < kD / 32; ++c) pass1(std::integral_constant<int, 32>{}, c * 32);
-      pass1(std::integral_constant<int, 16>{}, (kD / 32) * 32);
+      for (int c = 0; c < kHalfCols / 32; ++c) pass1(std::integral_constant<int, 32>{}, c * 32);
+      pass1(std::integral_constant<int, 8>{}, (kHalfCols / 32) * 32);
+      sstat[half * kBM + row_in_tile] = make_float2(sum, sq);
       tmem_wait_st();
-      const float mean = sum * (1.0f / kD);
+      named_bar_sync(1, kEpiThreads);                  // both halves of every row have published their partials
+      const float2 other = sstat[(half ^ 1) * kBM + row_in_tile];
+      const float mean = (sum + other.x) * (1.0f / kD);
+      const float var = fmaxf((sq + other.y) * (1.0f / kD) - mean * mean, 0.0f);
+      const float rstd = 1.0f / sqrtf(var + 1e-5f);
 
-      // pass 2: centred variance (two-pass, like torch's LayerNorm moments)
-      float var = 0.0f;
+      // pass 2: normalise, scale/shift, store
+      const float gadd = p.adaln ? 1.0f : 0.0f;
       auto pass2 = [&](auto width_tag, int c0) {
         constexpr int W = decltype(width_tag)::value;
         uint32_t r[32];
         tmem_ld<W>(taddr + c0, r);
-        tmem_wait_ld();
+        float4 gs[W / 4], hs[W / 4];
 #pragma unroll
-        for (int j = 0; j < W; ++j) { const float d = __uint_as_float(r[j]) - mean; var = fmaf(d, d, var); }
-      };
-#pragma unroll 1
-      for (int c = 0; c < kD / 32; ++c) pass2(std::integral_constant<int, 32>{}, c * 32);
-      pass2(std::integral_constant<int, 16>{}, (kD / 32) * 32);
-      const float rstd = 1.0f / sqrtf(var * (1.0f / kD) + 1e-5f);
-
-      // pass 3: normalise, scale/shift, store
-      const float gadd = p.adaln ? 1.0f : 0.0f;
-      auto pass3 = [&](auto width_tag, int c0) {
-        constexpr int W = decltype(width_tag)::value;
-        uint32_t r[32];
-        tmem_ld<W>(taddr + c0, r);
+        for (int j = 0; j < W / 4; ++j) {
+          gs[j] = __ldg(reinterpret_cast<const float4*>(p.ln_scale + col0 + c0) + j);
+          hs[j] = __ldg(reinterpret_cast<const float4*>(p.ln_shift + col0 + c0) + j);
+        }
         tmem_wait_ld();
         float v[W];
 #pragma unroll
-        for (int j = 0; j < W; ++j) {
-          const float g = __ldg(p.ln_scale + c0 + j) + gadd;
-          v[j] = (__uint_as_float(r[j]) - mean) * rstd * g + __ldg(p.ln_shift + c0 + j);
+        for (int j = 0; j < W / 4; ++j) {
+          v[4 * j + 0] = (__uint_as_float(r[4 * j + 0]) - mean) * rstd * (gs[j].x + gadd) + hs[j].x;
+          v[4 * j + 1] = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * (gs[j].y + gadd) + hs[j].y;
+          v[4 * j + 2] = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * (gs[j].z + gadd) + hs[j].z;
+          v[4 * j + 3] = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * (gs[j].w + gadd) + hs[j].w;
         }
         if (p.out32 != nullptr) {
-          float4* dst = reinterpret_cast<float4*>(p.out32 + row * kD + c0);
+          float4* dst = reinterpret_cast<float4*>(p.out32 + row * kD + col0 + c0);
 #pragma unroll
           for (int j = 0; j < W / 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        uint4* dst16 = reinterpret_cast<uint4*>(static_cast<typename O::T*>(p.out16) + row * kD + c0);
+        uint4* dst16 = reinterpret_cast<uint4*>(static_cast<typename O::T*>(p.out16) + row * kD + col0 + c0);
 #pragma unroll
         for (int j = 0; j < W / 8; ++j)
           dst16[j] = make_uint4(O::pack(v[8 * j], v[8 * j + 1]), O::pack(v[8 * j + 2], v[8 * j + 3]),
                                 O::pack(v[8 * j + 4], v[8 * j + 5]), O::pack(v[8 * j + 6], v[8 * j + 7]));
       };
 #pragma unroll 1
-      for (int c = 0; c < kD / 32; ++c) pass3(std::integral_constant<int, 32>{}, c * 32);
-      pass3(std::integral_constant<int, 16>{}, (kD / 32) * 32);
+      for (int c = 0; c < kHalfCols / 32; ++c) pass2(std::integral_constant<int, 32>{}, c * 32);
+      pass2(std::integral_constant<int, 8>{}, (kHalfCols / 32) * 32);
 
       tc_fence_before();
       mbar_arrive(tempty);
