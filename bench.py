@@ -32,7 +32,7 @@ METRIC = "layouts_per_sec_T100_batch1024_N25"
 UNIT = "layouts/s"
 T = 100
 # algorithmic FLOPs per layout per launch (unpadded shapes, SURVEY.md 8d / BASELINE.md 3)
-FLOPS = {"qkv_gemm": 161_472_000, "outproj_ln_gemm": 53_824_000, "ff1_gemm": 215_296_000, "ff2_ln_gemm": 215_296_000,
+FLOPS = {"qkv_gemm": 161_472_000, "outproj_gemm": 53_824_000, "ff1_gemm": 215_296_000, "ff2_gemm": 215_296_000,
          "attention": 29_000_000, "head_gemm": 17_980_000}
 FLOPS_PER_LAYOUT_STEP = 2_717_532_000
 

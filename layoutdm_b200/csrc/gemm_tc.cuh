@@ -9,12 +9,13 @@
 //   warps 2..9 : epilogue; warp w owns TMEM lanes 32*(w%4)..+31 (thread = one output row) and one half of the
 //                tile's columns (two warps per scheduler, so one warp's TMEM/global latency hides behind the other)
 //
-// Two kernels:
-//   gemm_tc_kernel : N tiled (UMMA_N <= 256), double-buffered accumulators, epilogues
-//                    QKV (bias, q-scale) / FF1 (bias, ReLU) / head (fp32 logits)
-//   gemm_ln_kernel : the whole d_model = 464 row in one CTA (two MMAs 240 + 224 per k-step), epilogue
-//                    bias + residual + LayerNorm (affine or timestep-adaptive): two passes over the TMEM accumulator,
-//                    per-thread row statistics combined across the two column halves through shared memory.
+// gemm_tc_kernel : N tiled (UMMA_N <= 256), double-buffered TMEM accumulators so the epilogue of tile i overlaps the
+//                  main loop of tile i+1; epilogues QKV (bias, q-scale, 16-bit) / FF1 (bias, ReLU, 16-bit) /
+//                  fp32 (bias; out-projection, FF2 and the vocabulary head).  The epilogue touches global memory only
+//                  with stores: a 1-CTA/SM kernel with ~200 KB of smem has no L1 and only 8 epilogue warps to hide load
+//                  latency (round-1a/1b profiles: a residual+LayerNorm epilogue fused here ran 10x slower than the MMAs it
+//                  followed), so residual add + LayerNorm live in resid_ln_kernel (embed.cuh), a bandwidth-bound kernel
+//                  with full occupancy.
 //
 // Reference ops replaced: nn.Linear / nn.MultiheadAttention projections / nn.LayerNorm / AdaLayerNorm in
 // T/models/transformer_utils.py:79-83,165-210 and T/models/common/nn_lib.py:187-189,235.
@@ -194,206 +195,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Full-row GEMM + residual + LayerNorm
-// ---------------------------------------------------------------------------------------------------------
-constexpr int kD = 464;                     // d_model of the LayoutDM denoiser (512 * 29/32)
-constexpr int kLnN1 = 240, kLnN2 = 224;     // the two MMA widths covering 464 columns
-constexpr int kLnStages = 3;
-constexpr int kLnBTileBytes = kD * kBK * 2;               // 59392 = 58 * 1024
-constexpr int kLnStageBytes = kATileBytes + kLnBTileBytes; // 75776
-constexpr int kLnStatBytes = 2 * kBM * 8;          // per-row (sum, sumsq) partials of the two column halves
-constexpr int kLnSmemBytes = kLnStages * kLnStageBytes + 1024 + 256 + kLnStatBytes;
-
-struct GemmLnParams {
-  int M, K;
-  const float* bias;       // [464]
-  const float* resid;      // fp32 [M][464]
-  float* y_out;            // fp32 [M][464] pre-norm sum (the next residual) or nullptr
-  const float* ln_scale;   // [464]: gamma (affine) or AdaLN scale (then 1 + scale is applied)
-  const float* ln_shift;   // [464]: beta or AdaLN shift
-  int adaln;               // 1: out = norm * (1 + scale) + shift
-  float* out32;            // fp32 [M][464] normalised output (residual of the next block) or nullptr
-  void* out16;             // 16-bit [M][464] normalised output = next GEMM's A operand
-};
-
-template <bool BF16>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmLnParams p) {
-  static_assert(kLnBTileBytes % 1024 == 0 && (kLnN1 * kBK * 2) % 1024 == 0, "swizzle atom alignment");
-  constexpr uint32_t kTmemCols = 512;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kLnStages * kLnStageBytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kLnStages;
-  uint64_t* tfull = bars + 2 * kLnStages;
-  uint64_t* tempty = tfull + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 1);
-  float2* sstat = reinterpret_cast<float2*>(smem + kLnStages * kLnStageBytes + 256);   // [2 halves][128 rows]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = (p.K + kBK - 1) / kBK;
-  const int total_tiles = p.M / kBM;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_b);
-    for (int i = 0; i < kLnStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(tfull, 1);
-    mbar_init(tempty, kEpiThreads);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * kLnStageBytes;
-          mbar_arrive_expect_tx(&full[stage], kLnStageBytes);
-          tma_load_2d(sa, &map_a, &full[stage], kb * kBK, tile * kBM);
-          tma_load_2d(sa + kATileBytes, &map_b, &full[stage], kb * kBK, 0);                          // W rows 0..231
-          tma_load_2d(sa + kATileBytes + (kD / 2) * kBK * 2, &map_b, &full[stage], kb * kBK, kD / 2);  // rows 232..463
-          if (++stage == kLnStages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc_f16(kBM, kLnN1, BF16 ? 1 : 0);
-      constexpr uint32_t idesc2 = make_idesc_f16(kBM, kLnN2, BF16 ? 1 : 0);
-      int stage = 0; uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty, acc_phase ^ 1);
-        tc_fence_after();
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kLnStageBytes);
-          const uint64_t da = make_smem_desc_sw128(sa);
-          const uint64_t db1 = make_smem_desc_sw128(sa + kATileBytes);
-          const uint64_t db2 = make_smem_desc_sw128(sa + kATileBytes + kLnN1 * kBK * 2);
-          const int nk = min(kBK, p.K - kb * kBK) / kUmmaK;
-          for (int k = 0; k < nk; ++k) {
-            umma_f16(tmem_base, da + 2 * k, db1 + 2 * k, idesc1, (kb | k) != 0);
-            umma_f16(tmem_base + kLnN1, da + 2 * k, db2 + 2 * k, idesc2, (kb | k) != 0);
-          }
-          umma_commit(&empty[stage]);
-          if (++stage == kLnStages) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(tfull);
-        acc_phase ^= 1;
-      }
-    }
-  } else {
-    // ===================== epilogue: 8 warps = 4 lane quadrants x 2 column halves of 232 =====================
-    using O = OpT<BF16>;
-    const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int row_in_tile = quad * 32 + lane;
-    constexpr int kHalfCols = kD / 2;                 // 232 = 7 * 32 + 8
-    const int col0 = half * kHalfCols;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const size_t row = static_cast<size_t>(tile) * kBM + row_in_tile;
-      mbar_wait(tfull, acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + col0;
-      const float* rrow = p.resid + row * kD + col0;
-
-      // pass 1: y = acc + bias + resid ; y back to TMEM (and to y_out) ; partial row sum / sum of squares
-      float sum = 0.0f, sq = 0.0f;
-      auto pass1 = [&](auto width_tag, int c0) {
-        constexpr int W = decltype(width_tag)::value;
-        uint32_t r[32];
-        tmem_ld<W>(taddr + c0, r);
-        float4 rs[W / 4], bs[W / 4];
-#pragma unroll
-        for (int j = 0; j < W / 4; ++j) {
-          rs[j] = __ldg(reinterpret_cast<const float4*>(rrow + c0) + j);
-          bs[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0) + j);
-        }
-        tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < W / 4; ++j) {
-          float4 y;
-          y.x = __uint_as_float(r[4 * j + 0]) + bs[j].x + rs[j].x;
-          y.y = __uint_as_float(r[4 * j + 1]) + bs[j].y + rs[j].y;
-          y.z = __uint_as_float(r[4 * j + 2]) + bs[j].z + rs[j].z;
-          y.w = __uint_as_float(r[4 * j + 3]) + bs[j].w + rs[j].w;
-          sum += (y.x + y.y) + (y.z + y.w);
-          sq = fmaf(y.x, y.x, fmaf(y.y, y.y, fmaf(y.z, y.z, fmaf(y.w, y.w, sq))));
-          r[4 * j + 0] = __float_as_uint(y.x); r[4 * j + 1] = __float_as_uint(y.y);
-          r[4 * j + 2] = __float_as_uint(y.z); r[4 * j + 3] = __float_as_uint(y.w);
-          if (p.y_out != nullptr) reinterpret_cast<float4*>(p.y_out + row * kD + col0 + c0)[j] = y;
-        }
-        tmem_st<W>(taddr + c0, r);
-      };
-#pragma unroll 1
-      for (int c = 0; c < kHalfCols / 32; ++c) pass1(std::integral_constant<int, 32>{}, c * 32);
-      pass1(std::integral_constant<int, 8>{}, (kHalfCols / 32) * 32);
-      sstat[half * kBM + row_in_tile] = make_float2(sum, sq);
-      tmem_wait_st();
-      named_bar_sync(1, kEpiThreads);                  // both halves of every row have published their partials
-      const float2 other = sstat[(half ^ 1) * kBM + row_in_tile];
-      const float mean = (sum + other.x) * (1.0f / kD);
-      const float var = fmaxf((sq + other.y) * (1.0f / kD) - mean * mean, 0.0f);
-      const float rstd = 1.0f / sqrtf(var + 1e-5f);
-
-      // pass 2: normalise, scale/shift, store
-      const float gadd = p.adaln ? 1.0f : 0.0f;
-      auto pass2 = [&](auto width_tag, int c0) {
-        constexpr int W = decltype(width_tag)::value;
-        uint32_t r[32];
-        tmem_ld<W>(taddr + c0, r);
-        float4 gs[W / 4], hs[W / 4];
-#pragma unroll
-        for (int j = 0; j < W / 4; ++j) {
-          gs[j] = __ldg(reinterpret_cast<const float4*>(p.ln_scale + col0 + c0) + j);
-          hs[j] = __ldg(reinterpret_cast<const float4*>(p.ln_shift + col0 + c0) + j);
-        }
-        tmem_wait_ld();
-        float v[W];
-#pragma unroll
-        for (int j = 0; j < W / 4; ++j) {
-          v[4 * j + 0] = (__uint_as_float(r[4 * j + 0]) - mean) * rstd * (gs[j].x + gadd) + hs[j].x;
-          v[4 * j + 1] = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * (gs[j].y + gadd) + hs[j].y;
-          v[4 * j + 2] = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * (gs[j].z + gadd) + hs[j].z;
-          v[4 * j + 3] = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * (gs[j].w + gadd) + hs[j].w;
-        }
-        if (p.out32 != nullptr) {
-          float4* dst = reinterpret_cast<float4*>(p.out32 + row * kD + col0 + c0);
-#pragma unroll
-          for (int j = 0; j < W / 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        uint4* dst16 = reinterpret_cast<uint4*>(static_cast<typename O::T*>(p.out16) + row * kD + col0 + c0);
-#pragma unroll
-        for (int j = 0; j < W / 8; ++j)
-          dst16[j] = make_uint4(O::pack(v[8 * j], v[8 * j + 1]), O::pack(v[8 * j + 2], v[8 * j + 3]),
-                                O::pack(v[8 * j + 4], v[8 * j + 5]), O::pack(v[8 * j + 6], v[8 * j + 7]));
-      };
-#pragma unroll 1
-      for (int c = 0; c < kHalfCols / 32; ++c) pass2(std::integral_constant<int, 32>{}, c * 32);
-      pass2(std::integral_constant<int, 8>{}, (kHalfCols / 32) * 32);
-
-      tc_fence_before();
-      mbar_arrive(tempty);
-      acc_phase ^= 1;
     }
   }
 

@@ -108,7 +108,7 @@ struct LdmHandle {
   // workspace (device), sized for cap layouts
   int cap = 0;
   void *x16 = nullptr, *qkv16 = nullptr, *att16 = nullptr, *z16 = nullptr, *hid16 = nullptr;
-  float *x32 = nullptr, *y32 = nullptr, *logits = nullptr;
+  float *x32 = nullptr, *y32 = nullptr, *g32 = nullptr, *logits = nullptr;
   long long* ids[2] = {nullptr, nullptr};
   long long* ids_final = nullptr;
   long long *c_seq = nullptr, *c_seq_orig = nullptr; unsigned char* c_mask = nullptr; float* c_tbl = nullptr;  // staging for ldm_sample_host
@@ -172,7 +172,7 @@ void build_schedule(const LdmModelDesc& d, int N, float* out /*[8][T+1]*/) {
   }
 }
 
-enum : int { CAT_EMBED = 0, CAT_QKV, CAT_ATTN, CAT_OUTPROJ, CAT_FF1, CAT_FF2, CAT_HEAD, CAT_EPILOGUE, CAT_MISC, CAT_COUNT };
+enum : int { CAT_EMBED = 0, CAT_QKV, CAT_ATTN, CAT_OUTPROJ, CAT_FF1, CAT_FF2, CAT_HEAD, CAT_EPILOGUE, CAT_MISC, CAT_RESID_LN, CAT_COUNT };
 
 struct ProfScope {   // counts the launch; when profiling is on, brackets it with a CUDA-event pair on the launching stream
   LdmHandle* h; cudaStream_t st; cudaEvent_t b = nullptr;
@@ -196,7 +196,7 @@ int set_smem(K kernel, int bytes) {
 int ensure_workspace(LdmHandle* h, int n_layouts) {
   if (n_layouts <= h->cap) return LDM_OK;
   // free the old workspace
-  void* olds[] = {h->x16, h->qkv16, h->att16, h->z16, h->hid16, h->x32, h->y32, h->logits, h->ids[0], h->ids[1], h->ids_final, h->c_seq, h->c_seq_orig, h->c_mask};
+  void* olds[] = {h->x16, h->qkv16, h->att16, h->z16, h->hid16, h->x32, h->y32, h->g32, h->logits, h->ids[0], h->ids[1], h->ids_final, h->c_seq, h->c_seq_orig, h->c_mask};
   for (void* p : olds) if (p) cudaFree(p);
   const size_t M = static_cast<size_t>(n_layouts) * kBM;
   const int d = h->desc.d_model, ff = h->desc.d_ff;
@@ -207,6 +207,7 @@ int ensure_workspace(LdmHandle* h, int n_layouts) {
   CK(cudaMalloc(&h->hid16, M * ff * 2));
   CK(cudaMalloc(reinterpret_cast<void**>(&h->x32), M * d * 4));
   CK(cudaMalloc(reinterpret_cast<void**>(&h->y32), M * d * 4));
+  CK(cudaMalloc(reinterpret_cast<void**>(&h->g32), M * d * 4));
   CK(cudaMalloc(reinterpret_cast<void**>(&h->logits), M * kLogitLd * 4));
   const size_t nid = static_cast<size_t>(n_layouts) * h->S;
   CK(cudaMalloc(reinterpret_cast<void**>(&h->ids[0]), nid * 8));
@@ -253,10 +254,16 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       attention_kernel<BF16><<<n * h->desc.n_heads, kAttThreads, kAttSmemBytes, st>>>(h->qkv16, h->att16, h->S, d / h->desc.n_heads, h->desc.n_heads);
     }
     LDM_STAGE_DONE();
-    {  // out-projection + residual (normalised x) + LayerNorm2
-      GemmLnParams p{M, d, h->bo[l], h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr, h->z16};
+    {  // out-projection (+bias) -> fp32
+      GemmParams p{M, d, d, d / kFF1Tile, h->bo[l], h->g32, d, 1.0f, 0};
+      const int tiles = n * p.n_tiles;
       ProfScope ps(h, CAT_OUTPROJ, st);
-      gemm_ln_kernel<BF16><<<std::min(n, sms), kGemmThreads, kLnSmemBytes, st>>>(h->m_att16, h->m_wo[l], p);
+      gemm_tc_kernel<kFF1Tile, 240, 4, EPI_F32, BF16><<<std::min(tiles, sms), kGemmThreads, GemmSmem<240, 4>::kBytes, st>>>(h->m_att16, h->m_wo[l], p);
+    }
+    LDM_STAGE_DONE();
+    {  // y = g + x (residual from the NORMALISED x) ; z = LayerNorm2(y)
+      ProfScope ps(h, CAT_RESID_LN, st);
+      resid_ln_kernel<BF16><<<(M * 32 + 255) / 256, 256, 0, st>>>(h->g32, h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr, h->z16, M, d);
     }
     LDM_STAGE_DONE();
     {  // FF1 + ReLU
@@ -266,17 +273,21 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       gemm_tc_kernel<kFF1Tile, 240, 4, EPI_RELU, BF16><<<std::min(tiles, sms), kGemmThreads, GemmSmem<240, 4>::kBytes, st>>>(h->m_z16, h->m_w1[l], p);
     }
     LDM_STAGE_DONE();
-    {  // FF2 + residual + (next block's AdaLN | head LayerNorm)
-      GemmLnParams p{};
-      p.M = M; p.K = ff; p.bias = h->b2[l]; p.resid = h->y32; p.y_out = nullptr;
+    {  // FF2 (+bias) -> fp32
+      GemmParams p{M, d, ff, d / kFF1Tile, h->b2[l], h->g32, d, 1.0f, 0};
+      const int tiles = n * p.n_tiles;
+      ProfScope ps(h, CAT_FF2, st);
+      gemm_tc_kernel<kFF1Tile, 240, 4, EPI_F32, BF16><<<std::min(tiles, sms), kGemmThreads, GemmSmem<240, 4>::kBytes, st>>>(h->m_hid16, h->m_w2[l], p);
+    }
+    LDM_STAGE_DONE();
+    {  // h = g + y ; next block's AdaLN(h, t) (fp32 residual + 16-bit operand) or the head LayerNorm
+      ProfScope ps(h, CAT_RESID_LN, st);
       if (l + 1 < L) {
         const float* tab = h->adaln + (static_cast<size_t>(l + 1) * T + t_model) * 2 * d;
-        p.ln_scale = tab; p.ln_shift = tab + d; p.adaln = 1; p.out32 = h->x32; p.out16 = h->x16;
+        resid_ln_kernel<BF16><<<(M * 32 + 255) / 256, 256, 0, st>>>(h->g32, h->y32, nullptr, tab, tab + d, 1, h->x32, h->x16, M, d);
       } else {
-        p.ln_scale = h->hlnw; p.ln_shift = h->hlnb; p.adaln = 0; p.out32 = nullptr; p.out16 = h->z16;
+        resid_ln_kernel<BF16><<<(M * 32 + 255) / 256, 256, 0, st>>>(h->g32, h->y32, nullptr, h->hlnw, h->hlnb, 0, nullptr, h->z16, M, d);
       }
-      ProfScope ps(h, CAT_FF2, st);
-      gemm_ln_kernel<BF16><<<std::min(n, sms), kGemmThreads, kLnSmemBytes, st>>>(h->m_hid16, h->m_w2[l], p);
     }
     LDM_STAGE_DONE();
   }
@@ -360,7 +371,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   if (!desc || !w || !out) return fail(LDM_ERR_INVALID, "null argument");
   const int d = desc->d_model, ff = desc->d_ff, L = desc->n_layers, T = desc->num_timesteps;
   const int C = desc->n_cat + 4 * desc->n_bins + 2, S = desc->n_elem * desc->n_attr;
-  if (d != kD || desc->n_heads != 8 || ff != 8 * kFF1Tile)
+  if (d != 2 * kFF1Tile || desc->n_heads != 8 || ff != 8 * kFF1Tile)
     return fail(LDM_ERR_UNSUPPORTED, "kernels are built for d_model=464, 8 heads, d_ff=1856 (got %d, %d, %d)", d, desc->n_heads, ff);
   if (L < 1 || L > kMaxLayers || T < 2) return fail(LDM_ERR_UNSUPPORTED, "n_layers must be in [1,%d], T >= 2", kMaxLayers);
   if (C < 129 || C > kLogitLd || S > 125 || S < 1 || desc->n_attr > kMaxAttr || desc->n_attr < 1)
@@ -425,9 +436,9 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
     TRY(dev_upload(h, &h->ln2w[l], w->norm2_w + static_cast<size_t>(l) * d, static_cast<size_t>(d)));
     TRY(dev_upload(h, &h->ln2b[l], w->norm2_b + static_cast<size_t>(l) * d, static_cast<size_t>(d)));
     TRY(make_map(&h->m_wqkv[l], h->wqkv[l], kQkvN, d, 256, h->bf16));
-    TRY(make_map(&h->m_wo[l], h->wo[l], d, d, kD / 2, h->bf16));
+    TRY(make_map(&h->m_wo[l], h->wo[l], d, d, 240, h->bf16));
     TRY(make_map(&h->m_w1[l], h->w1[l], ff, d, 240, h->bf16));
-    TRY(make_map(&h->m_w2[l], h->w2[l], d, ff, kD / 2, h->bf16));
+    TRY(make_map(&h->m_w2[l], h->w2[l], d, ff, 240, h->bf16));
   }
   {
     float* tmp = nullptr;
@@ -453,13 +464,13 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
     TRY((set_smem(gemm_tc_kernel<256, 256, 4, EPI_QKV, true>, GemmSmem<256, 4>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 4, EPI_RELU, true>, GemmSmem<240, 4>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<160, 160, 4, EPI_F32, true>, GemmSmem<160, 4>::kBytes)));
-    TRY((set_smem(gemm_ln_kernel<true>, kLnSmemBytes)));
+    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 4, EPI_F32, true>, GemmSmem<240, 4>::kBytes)));
     TRY((set_smem(attention_kernel<true>, kAttSmemBytes)));
   } else {
     TRY((set_smem(gemm_tc_kernel<256, 256, 4, EPI_QKV, false>, GemmSmem<256, 4>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 4, EPI_RELU, false>, GemmSmem<240, 4>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<160, 160, 4, EPI_F32, false>, GemmSmem<160, 4>::kBytes)));
-    TRY((set_smem(gemm_ln_kernel<false>, kLnSmemBytes)));
+    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 4, EPI_F32, false>, GemmSmem<240, 4>::kBytes)));
     TRY((set_smem(attention_kernel<false>, kAttSmemBytes)));
   }
 #undef TRY
@@ -471,7 +482,7 @@ int ldm_destroy(LdmHandle* h) {
   if (!h) return LDM_OK;
   cudaSetDevice(h->desc.device);
   for (void* p : h->owned) cudaFree(p);
-  void* ws[] = {h->x16, h->qkv16, h->att16, h->z16, h->hid16, h->x32, h->y32, h->logits, h->ids[0], h->ids[1], h->ids_final, h->c_seq, h->c_seq_orig, h->c_mask, h->c_tbl};
+  void* ws[] = {h->x16, h->qkv16, h->att16, h->z16, h->hid16, h->x32, h->y32, h->g32, h->logits, h->ids[0], h->ids[1], h->ids_final, h->c_seq, h->c_seq_orig, h->c_mask, h->c_tbl};
   for (void* p : ws) if (p) cudaFree(p);
   delete h;
   return LDM_OK;
@@ -603,6 +614,7 @@ int64_t ldm_debug_read(const LdmHandle* h, const char* name, void* dst, int64_t 
   const void* src = nullptr; size_t bytes = 0;
   if (!strcmp(name, "x32")) { src = h->x32; bytes = M * d * 4; }
   else if (!strcmp(name, "y32")) { src = h->y32; bytes = M * d * 4; }
+  else if (!strcmp(name, "g32")) { src = h->g32; bytes = M * d * 4; }
   else if (!strcmp(name, "x16")) { src = h->x16; bytes = M * d * 2; }
   else if (!strcmp(name, "z16")) { src = h->z16; bytes = M * d * 2; }
   else if (!strcmp(name, "att16")) { src = h->att16; bytes = M * d * 2; }
