@@ -75,6 +75,19 @@ LDM_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* ba
       : "memory");
 }
 
+// multicast variant: the tile lands at the same smem offset (and signals the same-offset mbarrier) in every CTA of `mask`
+LDM_DEVINL void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+LDM_DEVINL uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+LDM_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, loads/stores, fences
 // ------------------------------------------------------------------------------------------------------------
@@ -102,6 +115,12 @@ LDM_DEVINL void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint
 // mbarrier arrive once all previously issued tcgen05 async ops of this thread are complete
 LDM_DEVINL void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// same, arriving on the same-offset mbarrier of every CTA in `mask` (cluster multicast pipelines)
+LDM_DEVINL void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 
 // Shared-memory matrix descriptor, K-major operand tile stored as rows of 64 x 16-bit (128 B) with the

@@ -45,17 +45,17 @@ template <bool BF16>
 __global__ void __launch_bounds__(256)
 embed_adaln_kernel(const long long* __restrict__ ids /*[B][S]*/, const float* __restrict__ cat_emb /*[C][d]*/,
                    const float* __restrict__ pos /*[S][d]*/, const float* __restrict__ adaln /*[2d] for (layer 0, t)*/,
-                   float* __restrict__ x32 /*[B*128][d]*/, void* __restrict__ x16_, int n_layouts, int S, int d) {
+                   float* __restrict__ x32 /*[B*128][d]*/, void* __restrict__ x16_, int n_layouts, int n_layouts_padded, int S, int d) {
   using O = OpT<BF16>;
   typename O::T* x16 = static_cast<typename O::T*>(x16_);
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp_global >= n_layouts * 128) return;
+  if (warp_global >= n_layouts_padded * 128) return;
   const int b = warp_global >> 7, s = warp_global & 127;
   const size_t row = static_cast<size_t>(warp_global);
   const int nv = d / 4;                      // float4 per row (464 / 4 = 116)
   float4* o32 = reinterpret_cast<float4*>(x32 + row * d);
   uint2* o16 = reinterpret_cast<uint2*>(x16 + row * d);
-  if (s >= S) {
+  if (s >= S || b >= n_layouts) {      // padding rows / padding layout of an odd batch
     for (int i = lane; i < nv; i += 32) { o32[i] = make_float4(0.f, 0.f, 0.f, 0.f); o16[i] = make_uint2(0u, 0u); }
     return;
   }

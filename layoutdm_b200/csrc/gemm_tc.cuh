@@ -52,8 +52,11 @@ struct GemmSmem {
   static constexpr int kBytes = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
 };
 
+// Launched as thread-block clusters of 2 CTAs along M: the pair works on M-blocks (2p, 2p+1) of the same N-tile, each CTA
+// TMA-loads its own A tile and HALF of the shared weight tile, multicast into both CTAs' shared memory -- the weight
+// traffic out of L2 halves (round-1c: the K=464 GEMMs were bound by ~8.3 TB/s of L2->SM traffic, not by the tensor pipe).
 template <int BN_STORE, int UMMA_N, int STAGES, int EPI, bool BF16>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
   using SM = GemmSmem<UMMA_N, STAGES>;
   static_assert(UMMA_N % 16 == 0 && UMMA_N <= 256 && BN_STORE <= UMMA_N, "invalid UMMA shape");
@@ -73,19 +76,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + kBK - 1) / kBK;
-  const int total_tiles = (p.M / kBM) * p.n_tiles;
+  const uint32_t cta_rank = cluster_ctarank();               // 0 / 1 inside the pair
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int total_tiles = (p.M / (2 * kBM)) * p.n_tiles;     // tiles per pair: (256-row block, N-tile)
+  constexpr int kHalfRows = UMMA_N / 2;                      // weight rows each CTA loads and multicasts
+  static_assert((kHalfRows * kBK * 2) % 1024 == 0, "half weight tile must stay swizzle-atom aligned");
   for (int i = threadIdx.x; i < p.N; i += kGemmThreads) sbias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.0f;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }   // empty: both CTAs' MMAs released the stage
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiThreads); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                                        // peer's barriers are initialised before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -93,14 +101,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        const int m_blk = 2 * (tile / p.n_tiles) + static_cast<int>(cta_rank), n_blk = tile % p.n_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_wait(&empty[stage], phase ^ 1);               // both CTAs are done reading this stage
           uint8_t* sa = smem + stage * SM::kStageBytes;
-          mbar_arrive_expect_tx(&full[stage], SM::kStageBytes);
+          mbar_arrive_expect_tx(&full[stage], SM::kStageBytes);   // own A + both halves of the weight tile
           tma_load_2d(sa, &map_a, &full[stage], kb * kBK, m_blk * kBM);
-          tma_load_2d(sa + kATileBytes, &map_b, &full[stage], kb * kBK, n_blk * BN_STORE);
+          tma_load_2d_mc(sa + kATileBytes + cta_rank * (kHalfRows * kBK * 2), &map_b, &full[stage], kb * kBK,
+                         n_blk * BN_STORE + static_cast<int>(cta_rank) * kHalfRows, static_cast<uint16_t>(0b11));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -111,7 +120,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr uint32_t idesc = make_idesc_f16(kBM, UMMA_N, BF16 ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
@@ -124,7 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int nk = min(kBK, p.K - kb * kBK) / kUmmaK;     // K tail: TMA zero-fills, skip the zero k-steps
           for (int k = 0; k < nk; ++k)
             umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);   // +32 B per k-step (>>4 = 2)
-          umma_commit(&empty[stage]);
+          umma_commit_mc(&empty[stage], static_cast<uint16_t>(0b11));   // release the stage in BOTH CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);
@@ -140,8 +149,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int kSplit = (kFull + 1) / 2;    // half 0: chunks [0, kSplit), half 1: [kSplit, kFull) + remainder
     static_assert(kRem == 0 || kRem == 8 || kRem == 16, "unsupported tile width");
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+      const int m_blk = 2 * (tile / p.n_tiles) + static_cast<int>(cta_rank), n_blk = tile % p.n_tiles;
       const int n0 = n_blk * BN_STORE;
       const size_t row = static_cast<size_t>(m_blk) * kBM + row_in_tile;
       float tile_scale = 1.0f;
@@ -200,6 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                                        // nobody exits while the peer may still multicast / arrive here
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 

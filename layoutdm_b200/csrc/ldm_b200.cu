@@ -194,6 +194,7 @@ int set_smem(K kernel, int bytes) {
 }
 
 int ensure_workspace(LdmHandle* h, int n_layouts) {
+  n_layouts = (n_layouts + 1) & ~1;     // GEMM CTA pairs work on 256-row blocks: keep an even number of layout tiles
   if (n_layouts <= h->cap) return LDM_OK;
   // free the old workspace
   void* olds[] = {h->x16, h->qkv16, h->att16, h->z16, h->hid16, h->x32, h->y32, h->g32, h->logits, h->ids[0], h->ids[1], h->ids_final, h->c_seq, h->c_seq_orig, h->c_mask};
@@ -216,6 +217,10 @@ int ensure_workspace(LdmHandle* h, int n_layouts) {
   CK(cudaMalloc(reinterpret_cast<void**>(&h->c_seq), nid * 8));
   CK(cudaMalloc(reinterpret_cast<void**>(&h->c_seq_orig), nid * 8));
   CK(cudaMalloc(reinterpret_cast<void**>(&h->c_mask), nid));
+  // zero once: the padding layout (odd batch sizes) and the 3 padding rows of every layout tile must stay finite
+  CK(cudaMemset(h->x16, 0, M * d * 2)); CK(cudaMemset(h->qkv16, 0, M * kQkvN * 2)); CK(cudaMemset(h->att16, 0, M * d * 2));
+  CK(cudaMemset(h->z16, 0, M * d * 2)); CK(cudaMemset(h->hid16, 0, M * ff * 2)); CK(cudaMemset(h->x32, 0, M * d * 4));
+  CK(cudaMemset(h->y32, 0, M * d * 4)); CK(cudaMemset(h->g32, 0, M * d * 4));
   CK(cudaMemset(h->logits, 0, M * kLogitLd * 4));
   h->cap = n_layouts;
   int rc;
@@ -229,36 +234,36 @@ int ensure_workspace(LdmHandle* h, int n_layouts) {
 template <bool BF16>
 int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, cudaStream_t st) {
   const int d = h->desc.d_model, ff = h->desc.d_ff, L = h->L, T = h->T;
-  const int M = n * kBM;
-  const int sms = h->num_sms;
+  const int np = (n + 1) & ~1;            // layouts incl. the padding layout of an odd batch
+  const int M = np * kBM;
+  const int sms = h->num_sms & ~1;        // CTA pairs
+  auto pair_grid = [&](int n_tiles) { return std::min((np / 2) * n_tiles * 2, sms); };
   int done = 0;
   // test tap: stop after `debug_stop_after` launches
 #define LDM_STAGE_DONE() do { if (h->debug_stop_after && ++done >= h->debug_stop_after) { CK(cudaGetLastError()); return LDM_OK; } } while (0)
   {
-    const int warps = n * 128, blocks = (warps * 32 + 255) / 256;
+    const int warps = np * 128, blocks = (warps * 32 + 255) / 256;
     ProfScope ps(h, CAT_EMBED, st);
     embed_adaln_kernel<BF16><<<blocks, 256, 0, st>>>(ids_in, h->cat_emb, h->pos, h->adaln + (static_cast<size_t>(0) * T + t_model) * 2 * d,
-                                                     h->x32, h->x16, n, h->S, d);
+                                                     h->x32, h->x16, n, np, h->S, d);
   }
   LDM_STAGE_DONE();
   for (int l = 0; l < L; ++l) {
     {  // QKV projection (+bias, q * 1/sqrt(head_dim))
       GemmParams p{M, kQkvN, d, kQkvN / 256, h->bqkv[l], h->qkv16, kQkvN, 1.0f / sqrtf(static_cast<float>(d / h->desc.n_heads)), 8 * kHeadPad};
-      const int tiles = n * p.n_tiles;
       ProfScope ps(h, CAT_QKV, st);
-      gemm_tc_kernel<256, 256, 4, EPI_QKV, BF16><<<std::min(tiles, sms), kGemmThreads, GemmSmem<256, 4>::kBytes, st>>>(h->m_x16, h->m_wqkv[l], p);
+      gemm_tc_kernel<256, 256, 4, EPI_QKV, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 4>::kBytes, st>>>(h->m_x16, h->m_wqkv[l], p);
     }
     LDM_STAGE_DONE();
     {
       ProfScope ps(h, CAT_ATTN, st);
-      attention_kernel<BF16><<<n * h->desc.n_heads, kAttThreads, kAttSmemBytes, st>>>(h->qkv16, h->att16, h->S, d / h->desc.n_heads, h->desc.n_heads);
+      attention_kernel<BF16><<<np * h->desc.n_heads, kAttThreads, kAttSmemBytes, st>>>(h->qkv16, h->att16, h->S, d / h->desc.n_heads, h->desc.n_heads);
     }
     LDM_STAGE_DONE();
     {  // out-projection (+bias) -> fp32
       GemmParams p{M, d, d, d / kFF1Tile, h->bo[l], h->g32, d, 1.0f, 0};
-      const int tiles = n * p.n_tiles;
       ProfScope ps(h, CAT_OUTPROJ, st);
-      gemm_tc_kernel<kFF1Tile, 240, 4, EPI_F32, BF16><<<std::min(tiles, sms), kGemmThreads, GemmSmem<240, 4>::kBytes, st>>>(h->m_att16, h->m_wo[l], p);
+      gemm_tc_kernel<kFF1Tile, 240, 4, EPI_F32, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 4>::kBytes, st>>>(h->m_att16, h->m_wo[l], p);
     }
     LDM_STAGE_DONE();
     {  // y = g + x (residual from the NORMALISED x) ; z = LayerNorm2(y)
@@ -268,16 +273,14 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     LDM_STAGE_DONE();
     {  // FF1 + ReLU
       GemmParams p{M, ff, d, ff / kFF1Tile, h->b1[l], h->hid16, ff, 1.0f, 0};
-      const int tiles = n * p.n_tiles;
       ProfScope ps(h, CAT_FF1, st);
-      gemm_tc_kernel<kFF1Tile, 240, 4, EPI_RELU, BF16><<<std::min(tiles, sms), kGemmThreads, GemmSmem<240, 4>::kBytes, st>>>(h->m_z16, h->m_w1[l], p);
+      gemm_tc_kernel<kFF1Tile, 240, 4, EPI_RELU, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 4>::kBytes, st>>>(h->m_z16, h->m_w1[l], p);
     }
     LDM_STAGE_DONE();
     {  // FF2 (+bias) -> fp32
       GemmParams p{M, d, ff, d / kFF1Tile, h->b2[l], h->g32, d, 1.0f, 0};
-      const int tiles = n * p.n_tiles;
       ProfScope ps(h, CAT_FF2, st);
-      gemm_tc_kernel<kFF1Tile, 240, 4, EPI_F32, BF16><<<std::min(tiles, sms), kGemmThreads, GemmSmem<240, 4>::kBytes, st>>>(h->m_hid16, h->m_w2[l], p);
+      gemm_tc_kernel<kFF1Tile, 240, 4, EPI_F32, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 4>::kBytes, st>>>(h->m_hid16, h->m_w2[l], p);
     }
     LDM_STAGE_DONE();
     {  // h = g + y ; next block's AdaLN(h, t) (fp32 residual + 16-bit operand) or the head LayerNorm
@@ -294,7 +297,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
   {  // vocabulary head -> fp32 logits
     GemmParams p{M, kLogitLd, d, 1, nullptr, h->logits, kLogitLd, 1.0f, 0};
     ProfScope ps(h, CAT_HEAD, st);
-    gemm_tc_kernel<160, 160, 4, EPI_F32, BF16><<<std::min(n, sms), kGemmThreads, GemmSmem<160, 4>::kBytes, st>>>(h->m_z16, h->m_whead, p);
+    gemm_tc_kernel<160, 160, 4, EPI_F32, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<160, 4>::kBytes, st>>>(h->m_z16, h->m_whead, p);
   }
 #undef LDM_STAGE_DONE
   CK(cudaGetLastError());
@@ -435,10 +438,10 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
     TRY(dev_upload(h, &h->b2[l], w->linear2_b + static_cast<size_t>(l) * d, static_cast<size_t>(d)));
     TRY(dev_upload(h, &h->ln2w[l], w->norm2_w + static_cast<size_t>(l) * d, static_cast<size_t>(d)));
     TRY(dev_upload(h, &h->ln2b[l], w->norm2_b + static_cast<size_t>(l) * d, static_cast<size_t>(d)));
-    TRY(make_map(&h->m_wqkv[l], h->wqkv[l], kQkvN, d, 256, h->bf16));
-    TRY(make_map(&h->m_wo[l], h->wo[l], d, d, 240, h->bf16));
-    TRY(make_map(&h->m_w1[l], h->w1[l], ff, d, 240, h->bf16));
-    TRY(make_map(&h->m_w2[l], h->w2[l], d, ff, 240, h->bf16));
+    TRY(make_map(&h->m_wqkv[l], h->wqkv[l], kQkvN, d, 128, h->bf16));   // each CTA of a pair loads half of the weight tile
+    TRY(make_map(&h->m_wo[l], h->wo[l], d, d, 120, h->bf16));
+    TRY(make_map(&h->m_w1[l], h->w1[l], ff, d, 120, h->bf16));
+    TRY(make_map(&h->m_w2[l], h->w2[l], d, ff, 120, h->bf16));
   }
   {
     float* tmp = nullptr;
@@ -448,7 +451,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
     int* hmap_dev = nullptr;
     TRY(dev_upload(h, &hmap_dev, hmap.data(), hmap.size()));
     TRY(pack16(h, &h->whead, tmp, hmap_dev, kLogitLd, d, d));
-    TRY(make_map(&h->m_whead, h->whead, kLogitLd, d, kLogitLd, h->bf16));
+    TRY(make_map(&h->m_whead, h->whead, kLogitLd, d, kLogitLd / 2, h->bf16));
   }
   {
     std::vector<float> sch(static_cast<size_t>(h->G) * 8 * (T + 1));
