@@ -45,16 +45,19 @@ struct GemmParams {
 
 template <int UMMA_N, int STAGES>
 struct GemmSmem {
-  static constexpr int kBTileBytes = UMMA_N * kBK * 2;
-  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static_assert(kBTileBytes % 1024 == 0, "B tile must keep 1024-B (swizzle atom) alignment");
+  static constexpr int kBHalfBytes = (UMMA_N / 2) * kBK * 2;     // each CTA of the pair holds half of the weight tile
+  static constexpr int kStageBytes = kATileBytes + kBHalfBytes;
+  static_assert(kBHalfBytes % 1024 == 0, "half weight tile must keep 1024-B (swizzle atom) alignment");
   static constexpr int kBiasBytes = 1856 * 4;   // the whole bias vector of the layer lives in smem
   static constexpr int kBytes = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
 };
 
-// Launched as thread-block clusters of 2 CTAs along M: the pair works on M-blocks (2p, 2p+1) of the same N-tile, each CTA
-// TMA-loads its own A tile and HALF of the shared weight tile, multicast into both CTAs' shared memory -- the weight
-// traffic out of L2 halves (round-1c: the K=464 GEMMs were bound by ~8.3 TB/s of L2->SM traffic, not by the tensor pipe).
+// CTA pairs (thread-block cluster of 2, cta_group::2): the pair computes a 256 x UMMA_N tile per step with ONE
+// tcgen05.mma issued by the leader CTA (rank 0): A = 128 rows from each CTA's own smem, B = UMMA_N/2 weight rows from each
+// CTA's smem, D = 128 accumulator rows in each CTA's TMEM.  Per CTA and k-block only 16 KB (A) + ~15 KB (half of B) enter
+// shared memory for 480 tensor-core cycles: ~65 B/clk, inside what one SM can ingest.  (Round 1c/1d: with 1-CTA 128 x 240
+// tiles the 46 KB per k-block needed ~98 B/clk; every k-block took ~870 cycles instead of 480 -- with or without TMA
+// multicast, which only saves L2 reads, not the SM's ingest.)
 template <int BN_STORE, int UMMA_N, int STAGES, int EPI, bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
@@ -63,80 +66,80 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   static_assert(BN_STORE % 8 == 0, "store width");
   constexpr int kAccStride = 256;            // TMEM columns between the two accumulators
   constexpr uint32_t kTmemCols = 512;
+  constexpr int kHalfRows = UMMA_N / 2;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * SM::kStageBytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* tfull = bars + 2 * STAGES;
-  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint64_t* full = bars;                     // leader's copy is the live one: 2 producer arrivals + both CTAs' TMA bytes
+  uint64_t* empty = bars + STAGES;           // per CTA: released by the leader's multicast tcgen05.commit
+  uint64_t* tfull = bars + 2 * STAGES;       // per CTA: accumulator ready (multicast commit)
+  uint64_t* tempty = bars + 2 * STAGES + 2;  // leader's copy: 16 warp arrivals (8 epilogue warps x 2 CTAs)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* sbias = reinterpret_cast<float*>(smem + STAGES * SM::kStageBytes + 256);
+  static_assert((2 * STAGES + 4) * 8 + 4 <= 256, "barrier block overflow");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + kBK - 1) / kBK;
-  const uint32_t cta_rank = cluster_ctarank();               // 0 / 1 inside the pair
+  const uint32_t cta_rank = cluster_ctarank();               // 0 = leader
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int total_tiles = (p.M / (2 * kBM)) * p.n_tiles;     // tiles per pair: (256-row block, N-tile)
-  constexpr int kHalfRows = UMMA_N / 2;                      // weight rows each CTA loads and multicasts
-  static_assert((kHalfRows * kBK * 2) % 1024 == 0, "half weight tile must stay swizzle-atom aligned");
   for (int i = threadIdx.x; i < p.N; i += kGemmThreads) sbias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.0f;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }   // empty: both CTAs' MMAs released the stage
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiThreads); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  if (warp == 1) tmem_alloc_2cta(tmem_ptr, kTmemCols);
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();                                        // peer's barriers are initialised before any multicast lands
+  cluster_sync_all();                                        // both CTAs' barriers and TMEM are ready
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (one thread in each CTA) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
         const int m_blk = 2 * (tile / p.n_tiles) + static_cast<int>(cta_rank), n_blk = tile % p.n_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);               // both CTAs are done reading this stage
+          mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * SM::kStageBytes;
-          mbar_arrive_expect_tx(&full[stage], SM::kStageBytes);   // own A + both halves of the weight tile
-          tma_load_2d(sa, &map_a, &full[stage], kb * kBK, m_blk * kBM);
-          tma_load_2d_mc(sa + kATileBytes + cta_rank * (kHalfRows * kBK * 2), &map_b, &full[stage], kb * kBK,
-                         n_blk * BN_STORE + static_cast<int>(cta_rank) * kHalfRows, static_cast<uint16_t>(0b11));
+          const uint32_t lead_full = mapa_shared(smem_u32(&full[stage]), 0);
+          mbar_arrive_expect_tx_cluster(lead_full, SM::kStageBytes);
+          tma_load_2d_2cta(sa, &map_a, lead_full, kb * kBK, m_blk * kBM);
+          tma_load_2d_2cta(sa + kATileBytes, &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * kHalfRows);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(kBM, UMMA_N, BF16 ? 1 : 0);
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(2 * kBM, UMMA_N, BF16 ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        mbar_wait(&tempty[acc], acc_phase ^ 1);              // both CTAs drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait(&full[stage], phase);                    // both CTAs' A and B halves have landed
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * SM::kStageBytes);
           const uint64_t da = make_smem_desc_sw128(sa);
           const uint64_t db = make_smem_desc_sw128(sa + kATileBytes);
           const int nk = min(kBK, p.K - kb * kBK) / kUmmaK;     // K tail: TMA zero-fills, skip the zero k-steps
           for (int k = 0; k < nk; ++k)
-            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);   // +32 B per k-step (>>4 = 2)
-          umma_commit_mc(&empty[stage], static_cast<uint16_t>(0b11));   // release the stage in BOTH CTAs
+            umma_f16_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);   // +32 B per k-step (>>4 = 2)
+          umma_commit_2cta_mc(&empty[stage], static_cast<uint16_t>(0b11));       // free the stage in both CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        umma_commit_2cta_mc(&tfull[acc], static_cast<uint16_t>(0b11));           // accumulator ready in both CTAs
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -202,15 +205,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
 
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));   // leader's barrier: 8 warps x 2 CTAs
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();                                        // nobody exits while the peer may still multicast / arrive here
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+  cluster_sync_all();                                        // nobody exits while the peer may still arrive here / read our smem
+  if (warp == 1) { tc_fence_after(); tmem_dealloc_2cta(tmem_base, kTmemCols); }
 }
 
 }  // namespace ldm
