@@ -290,6 +290,22 @@ LDM_DEVINL uint4 philox4x32_10(uint4 c, uint2 k) {
 // u in (0,1): ((word >> 9) + 0.5) * 2^-23  (exact in fp32)
 LDM_DEVINL float u01_from_bits(uint32_t w) { return (static_cast<float>(w >> 9) + 0.5f) * 1.1920928955078125e-07f; }
 
+// explicit shared-space vector accesses (keeps them on the LDS/STS pipe; pointer arithmetic on the dynamic-smem base
+// otherwise degrades to generic LD/ST, which queue behind global traffic)
+LDM_DEVINL float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+LDM_DEVINL uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+LDM_DEVINL void sts_u4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 LDM_DEVINL float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -49,7 +49,8 @@ struct GemmSmem {
   static constexpr int kStageBytes = kATileBytes + kBHalfBytes;
   static_assert(kBHalfBytes % 1024 == 0, "half weight tile must keep 1024-B (swizzle atom) alignment");
   static constexpr int kBiasBytes = 1856 * 4;   // the whole bias vector of the layer lives in smem
-  static constexpr int kBytes = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
+  static constexpr int kXposeBytes = 8 * 4096;  // per-epilogue-warp 32 x 128 B transpose buffer for coalesced stores
+  static constexpr int kBytes = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes + kXposeBytes;
 };
 
 // CTA pairs (thread-block cluster of 2, cta_group::2): the pair computes a 256 x UMMA_N tile per step with ONE
@@ -148,6 +149,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;          // which half of the tile's columns
     const int row_in_tile = quad * 32 + lane;
+    const uint32_t sbias_addr = smem_u32(sbias);
+    const uint32_t xbuf = smem_u32(smem + STAGES * SM::kStageBytes + 256 + SM::kBiasBytes) + (warp - 2) * 4096;
     constexpr int kFull = BN_STORE / 32, kRem = BN_STORE % 32;
     constexpr int kSplit = (kFull + 1) / 2;    // half 0: chunks [0, kSplit), half 1: [kSplit, kFull) + remainder
     static_assert(kRem == 0 || kRem == 8 || kRem == 16, "unsupported tile width");
@@ -162,24 +165,77 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride;
 
-      auto do_chunk = [&](auto width_tag, int c0) {
-        constexpr int W = decltype(width_tag)::value;
+      // 32 accumulator columns -> registers -> (+bias, activation) -> this warp's smem transpose buffer -> row-contiguous
+      // 16-B global stores: every store instruction writes whole 64/128-byte row segments instead of 32 scattered 16-B
+      // pieces (round-1f profile: 38 % of epilogue stall cycles were LG-queue throttling on the scattered stores).
+      auto do_chunk32 = [&](int c0) {
         uint32_t r[32];
-        tmem_ld<W>(taddr + c0, r);
-        float bv[W];
+        tmem_ld<32>(taddr + c0, r);
+        float bv[32];
 #pragma unroll
-        for (int j = 0; j < W / 4; ++j) {      // smem broadcast reads overlap the TMEM load
-          const float4 b4 = *reinterpret_cast<const float4*>(sbias + n0 + c0 + 4 * j);
+        for (int j = 0; j < 8; ++j) {            // LDS broadcast reads overlap the TMEM load
+          const float4 b4 = lds_f4(sbias_addr + (n0 + c0 + 4 * j) * 4);
           bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
         }
         tmem_wait_ld();
-        float v[W];
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < W; ++j) {
+        for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(r[j]) + bv[j];
           if constexpr (EPI == EPI_QKV) x *= tile_scale;
           if constexpr (EPI == EPI_RELU) x = fmaxf(x, 0.0f);
           v[j] = x;
+        }
+        __syncwarp();                            // previous chunk's read-back of the buffer is complete
+        if constexpr (EPI == EPI_F32) {
+          // row = lane, 8 x 16-B pieces per 128-B row, piece c at (c ^ (lane & 7))
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            sts_u4(xbuf + lane * 128 + ((c ^ (lane & 7)) << 4),
+                   make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]), __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3])));
+          __syncwarp();
+          float* obase = static_cast<float*>(p.out) + (static_cast<size_t>(m_blk) * kBM + quad * 32) * p.ldo + n0 + c0;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {       // each instruction: 4 rows x 128 B
+            const int rr = it * 4 + (lane >> 3), c = lane & 7;
+            const uint4 d = lds_u4(xbuf + rr * 128 + ((c ^ (rr & 7)) << 4));
+            *reinterpret_cast<uint4*>(obase + static_cast<size_t>(rr) * p.ldo + c * 4) = d;
+          }
+        } else {
+          using O = OpT<BF16>;
+          // row = lane, 4 x 16-B pieces per 64-B row (two rows per 128 B), piece c at (c ^ ((lane >> 1) & 3))
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            sts_u4(xbuf + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4),
+                   make_uint4(O::pack(v[8 * c], v[8 * c + 1]), O::pack(v[8 * c + 2], v[8 * c + 3]),
+                              O::pack(v[8 * c + 4], v[8 * c + 5]), O::pack(v[8 * c + 6], v[8 * c + 7])));
+          __syncwarp();
+          typename O::T* obase = static_cast<typename O::T*>(p.out) + (static_cast<size_t>(m_blk) * kBM + quad * 32) * p.ldo + n0 + c0;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {       // each instruction: 8 rows x 64 B
+            const int rr = it * 8 + (lane >> 2), c = lane & 3;
+            const uint4 d = lds_u4(xbuf + rr * 64 + ((c ^ ((rr >> 1) & 3)) << 4));
+            *reinterpret_cast<uint4*>(obase + static_cast<size_t>(rr) * p.ldo + c * 8) = d;
+          }
+        }
+      };
+      // remainder columns (8 or 16): direct row stores
+      auto do_rem = [&](auto width_tag, int c0) {
+        constexpr int W = decltype(width_tag)::value;
+        uint32_t r[32];
+        tmem_ld<W>(taddr + c0, r);
+        tmem_wait_ld();
+        float v[W];
+#pragma unroll
+        for (int j = 0; j < W / 4; ++j) {
+          const float4 b4 = lds_f4(sbias_addr + (n0 + c0 + 4 * j) * 4);
+          v[4 * j] = __uint_as_float(r[4 * j]) + b4.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+          if constexpr (EPI == EPI_QKV) v[j] *= tile_scale;
+          if constexpr (EPI == EPI_RELU) v[j] = fmaxf(v[j], 0.0f);
         }
         if constexpr (EPI == EPI_F32) {
           float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row * p.ldo + n0 + c0);
@@ -196,12 +252,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       };
       if (half == 0) {
 #pragma unroll 1
-        for (int c = 0; c < kSplit; ++c) do_chunk(std::integral_constant<int, 32>{}, c * 32);
+        for (int c = 0; c < kSplit; ++c) do_chunk32(c * 32);
       } else {
 #pragma unroll 1
-        for (int c = kSplit; c < kFull; ++c) do_chunk(std::integral_constant<int, 32>{}, c * 32);
-        if constexpr (kRem == 16) do_chunk(std::integral_constant<int, 16>{}, kFull * 32);
-        if constexpr (kRem == 8) do_chunk(std::integral_constant<int, 8>{}, kFull * 32);
+        for (int c = kSplit; c < kFull; ++c) do_chunk32(c * 32);
+        if constexpr (kRem == 16) do_rem(std::integral_constant<int, 16>{}, kFull * 32);
+        if constexpr (kRem == 8) do_rem(std::integral_constant<int, 8>{}, kFull * 32);
       }
 
       tc_fence_before();

@@ -252,7 +252,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     {  // QKV projection (+bias, q * 1/sqrt(head_dim))
       GemmParams p{M, kQkvN, d, kQkvN / 256, h->bqkv[l], h->qkv16, kQkvN, 1.0f / sqrtf(static_cast<float>(d / h->desc.n_heads)), 8 * kHeadPad};
       ProfScope ps(h, CAT_QKV, st);
-      gemm_tc_kernel<256, 256, 6, EPI_QKV, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 6>::kBytes, st>>>(h->m_x16, h->m_wqkv[l], p);
+      gemm_tc_kernel<256, 256, 5, EPI_QKV, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 5>::kBytes, st>>>(h->m_x16, h->m_wqkv[l], p);
     }
     LDM_STAGE_DONE();
     {
@@ -263,7 +263,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     {  // out-projection (+bias) -> fp32
       GemmParams p{M, d, d, d / kFF1Tile, h->bo[l], h->g32, d, 1.0f, 0};
       ProfScope ps(h, CAT_OUTPROJ, st);
-      gemm_tc_kernel<kFF1Tile, 240, 6, EPI_F32, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 6>::kBytes, st>>>(h->m_att16, h->m_wo[l], p);
+      gemm_tc_kernel<kFF1Tile, 240, 5, EPI_F32, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 5>::kBytes, st>>>(h->m_att16, h->m_wo[l], p);
     }
     LDM_STAGE_DONE();
     {  // y = g + x (residual from the NORMALISED x) ; z = LayerNorm2(y)
@@ -274,13 +274,13 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     {  // FF1 + ReLU
       GemmParams p{M, ff, d, ff / kFF1Tile, h->b1[l], h->hid16, ff, 1.0f, 0};
       ProfScope ps(h, CAT_FF1, st);
-      gemm_tc_kernel<kFF1Tile, 240, 6, EPI_RELU, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 6>::kBytes, st>>>(h->m_z16, h->m_w1[l], p);
+      gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 5>::kBytes, st>>>(h->m_z16, h->m_w1[l], p);
     }
     LDM_STAGE_DONE();
     {  // FF2 (+bias) -> fp32
       GemmParams p{M, d, ff, d / kFF1Tile, h->b2[l], h->g32, d, 1.0f, 0};
       ProfScope ps(h, CAT_FF2, st);
-      gemm_tc_kernel<kFF1Tile, 240, 6, EPI_F32, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 6>::kBytes, st>>>(h->m_hid16, h->m_w2[l], p);
+      gemm_tc_kernel<kFF1Tile, 240, 5, EPI_F32, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 5>::kBytes, st>>>(h->m_hid16, h->m_w2[l], p);
     }
     LDM_STAGE_DONE();
     {  // h = g + y ; next block's AdaLN(h, t) (fp32 residual + 16-bit operand) or the head LayerNorm
@@ -297,7 +297,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
   {  // vocabulary head -> fp32 logits
     GemmParams p{M, kLogitLd, d, 1, nullptr, h->logits, kLogitLd, 1.0f, 0};
     ProfScope ps(h, CAT_HEAD, st);
-    gemm_tc_kernel<160, 160, 6, EPI_F32, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<160, 6>::kBytes, st>>>(h->m_z16, h->m_whead, p);
+    gemm_tc_kernel<160, 160, 5, EPI_F32, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<160, 5>::kBytes, st>>>(h->m_z16, h->m_whead, p);
   }
 #undef LDM_STAGE_DONE
   CK(cudaGetLastError());
@@ -464,16 +464,16 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   if (cudaDeviceSynchronize() != cudaSuccess) { ldm_destroy(h); return fail(LDM_ERR_CUDA, "weight packing failed: %s", cudaGetErrorString(cudaGetLastError())); }
 
   if (h->bf16) {
-    TRY((set_smem(gemm_tc_kernel<256, 256, 6, EPI_QKV, true>, GemmSmem<256, 6>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 6, EPI_RELU, true>, GemmSmem<240, 6>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<160, 160, 6, EPI_F32, true>, GemmSmem<160, 6>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 6, EPI_F32, true>, GemmSmem<240, 6>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, true>, GemmSmem<256, 5>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, true>, GemmSmem<240, 5>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, true>, GemmSmem<160, 5>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_F32, true>, GemmSmem<240, 5>::kBytes)));
     TRY((set_smem(attention_kernel<true>, kAttSmemBytes)));
   } else {
-    TRY((set_smem(gemm_tc_kernel<256, 256, 6, EPI_QKV, false>, GemmSmem<256, 6>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 6, EPI_RELU, false>, GemmSmem<240, 6>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<160, 160, 6, EPI_F32, false>, GemmSmem<160, 6>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 6, EPI_F32, false>, GemmSmem<240, 6>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, false>, GemmSmem<256, 5>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, false>, GemmSmem<240, 5>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, false>, GemmSmem<160, 5>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_F32, false>, GemmSmem<240, 5>::kBytes)));
     TRY((set_smem(attention_kernel<false>, kAttSmemBytes)));
   }
 #undef TRY
