@@ -31,7 +31,7 @@ constexpr int kGemmThreads = 320;
 constexpr int kEpiThreads = 256;   // warps 2..9
 constexpr int kATileBytes = kBM * kBK * 2;   // 16 KB
 
-enum : int { EPI_QKV = 0, EPI_RELU = 1, EPI_F32 = 2 };
+enum : int { EPI_QKV = 0, EPI_RELU = 1, EPI_F32 = 2, EPI_LN = 3 };
 
 struct GemmParams {
   int M, N, K;            // M multiple of 128; N = n_tiles * BN_STORE
@@ -41,6 +41,14 @@ struct GemmParams {
   int ldo;
   float qscale;           // EPI_QKV: columns < qcols are scaled by qscale after the bias
   int qcols;
+  // EPI_LN (N = 464 = 2 tiles of 232): y = acc + bias + resid ; out = LayerNorm(y) * gamma + beta  (gamma = 1 + scale_t for AdaLN)
+  const float* resid;     // fp32 [M][N] residual stream
+  float* y_out;           // fp32 [M][N] pre-norm sum (the next residual) or nullptr
+  const float* ln_scale;  // [N]
+  const float* ln_shift;  // [N]
+  int adaln;
+  float* out32;           // fp32 [M][N] normalised output (next residual, AdaLN case) or nullptr
+  void* out16;            // 16-bit [M][N] normalised output = next GEMM's A operand
 };
 
 template <int UMMA_N, int STAGES>
@@ -49,8 +57,9 @@ struct GemmSmem {
   static constexpr int kStageBytes = kATileBytes + kBHalfBytes;
   static_assert(kBHalfBytes % 1024 == 0, "half weight tile must keep 1024-B (swizzle atom) alignment");
   static constexpr int kBiasBytes = 1856 * 4;   // the whole bias vector of the layer lives in smem
-  static constexpr int kXposeBytes = 8 * 4096;  // per-epilogue-warp 32 x 128 B transpose buffer for coalesced stores
-  static constexpr int kBytes = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes + kXposeBytes;
+  static constexpr int kXposeBytes = 8 * 4096;  // per-epilogue-warp 32 x 128 B transpose buffer for coalesced loads/stores
+  static constexpr int kStatBytes = 2 * kBM * 8;  // EPI_LN: per-row (sum, sumsq) partials of the two column halves
+  static constexpr int kBytes = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes + kXposeBytes + kStatBytes;
 };
 
 // CTA pairs (thread-block cluster of 2, cta_group::2): the pair computes a 256 x UMMA_N tile per step with ONE
@@ -84,8 +93,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int num_kb = (p.K + kBK - 1) / kBK;
   const uint32_t cta_rank = cluster_ctarank();               // 0 = leader
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int total_tiles = (p.M / (2 * kBM)) * p.n_tiles;     // tiles per pair: (256-row block, N-tile)
-  for (int i = threadIdx.x; i < p.N; i += kGemmThreads) sbias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.0f;
+  const int n_super = p.M / (2 * kBM);                       // 256-row blocks; a pair walks all N tiles of a block in a row
+  for (int i = threadIdx.x; i < p.N; i += kGemmThreads) {
+    sbias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.0f;
+    if constexpr (EPI == EPI_LN) {
+      sbias[p.N + i] = __ldg(p.ln_scale + i) + (p.adaln ? 1.0f : 0.0f);
+      sbias[2 * p.N + i] = __ldg(p.ln_shift + i);
+    }
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -105,8 +120,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== TMA producer (one thread in each CTA) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-        const int m_blk = 2 * (tile / p.n_tiles) + static_cast<int>(cta_rank), n_blk = tile % p.n_tiles;
+      for (int sup = pair; sup < n_super; sup += n_pairs)
+      for (int n_blk = 0; n_blk < p.n_tiles; ++n_blk) {
+        const int m_blk = 2 * sup + static_cast<int>(cta_rank);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * SM::kStageBytes;
@@ -124,7 +140,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr uint32_t idesc = make_idesc_f16(2 * kBM, UMMA_N, BF16 ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+      for (int sup = pair; sup < n_super; sup += n_pairs)
+      for (int n_blk = 0; n_blk < p.n_tiles; ++n_blk) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);              // both CTAs drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
@@ -155,8 +172,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int kSplit = (kFull + 1) / 2;    // half 0: chunks [0, kSplit), half 1: [kSplit, kFull) + remainder
     static_assert(kRem == 0 || kRem == 8 || kRem == 16, "unsupported tile width");
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-      const int m_blk = 2 * (tile / p.n_tiles) + static_cast<int>(cta_rank), n_blk = tile % p.n_tiles;
+    if constexpr (EPI != EPI_LN) {
+    for (int sup = pair; sup < n_super; sup += n_pairs)
+    for (int n_blk = 0; n_blk < p.n_tiles; ++n_blk) {
+      const int m_blk = 2 * sup + static_cast<int>(cta_rank);
       const int n0 = n_blk * BN_STORE;
       const size_t row = static_cast<size_t>(m_blk) * kBM + row_in_tile;
       float tile_scale = 1.0f;
@@ -264,6 +283,188 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));   // leader's barrier: 8 warps x 2 CTAs
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+      } else {
+      // ============ fused residual + LayerNorm epilogue (out-projection / FF2) ============
+      // One CTA owns 128 complete rows (both 232-column tiles of a 256-row block run back to back on this pair).
+      //   phase A (per tile, overlaps the other tile's MMAs): y = acc + bias + resid -> back into TMEM (+ y_out), row sum / sumsq
+      //   phase B (after both tiles): LayerNorm from TMEM, 16-bit (+ fp32) outputs; then the accumulators are released.
+      // resid is read and every output is written through this warp's smem transpose buffer, i.e. as whole 64/128-byte
+      // row segments per instruction.
+      using O = OpT<BF16>;
+      static_assert(EPI != EPI_LN || (BN_STORE == 232 && kRem == 8), "LN epilogue is laid out for 2 x 232 columns");
+      float2* sstat = reinterpret_cast<float2*>(smem + STAGES * SM::kStageBytes + 256 + SM::kBiasBytes + SM::kXposeBytes);
+      const uint32_t sgamma_addr = sbias_addr + p.N * 4, sbeta_addr = sbias_addr + 2 * p.N * 4;
+      const int c_begin = half == 0 ? 0 : kSplit, c_end = half == 0 ? kSplit : kFull;   // 32-col chunks of each tile
+      for (int sup = pair; sup < n_super; sup += n_pairs) {
+        const int m_blk = 2 * sup + static_cast<int>(cta_rank);
+        const size_t row = static_cast<size_t>(m_blk) * kBM + row_in_tile;
+        const size_t wrow0 = static_cast<size_t>(m_blk) * kBM + quad * 32;      // first row of this warp
+        float sum = 0.0f, sq = 0.0f;
+        // ---------------- phase A ----------------
+        for (int n_blk = 0; n_blk < 2; ++n_blk) {
+          const int n0 = n_blk * BN_STORE;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + n_blk * kAccStride;
+          // prefetch the first chunk's residual rows while the MMAs are still running
+          uint4 q[8];
+          auto load_resid = [&](int c0) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + (lane >> 3), c = lane & 7;
+              q[it] = __ldg(reinterpret_cast<const uint4*>(p.resid + (wrow0 + rr) * p.N + n0 + c0 + c * 4));
+            }
+          };
+          load_resid(c_begin * 32);
+          mbar_wait(&tfull[n_blk], acc_phase);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = c_begin; c < c_end; ++c) {
+            const int c0 = c * 32;
+            uint32_t r[32];
+            tmem_ld<32>(taddr + c0, r);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + (lane >> 3), cc = lane & 7;
+              sts_u4(xbuf + rr * 128 + ((cc ^ (rr & 7)) << 4), q[it]);
+            }
+            __syncwarp();
+            float y[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 rs = lds_f4(xbuf + lane * 128 + ((j ^ (lane & 7)) << 4));
+              const float4 b4 = lds_f4(sbias_addr + (n0 + c0 + 4 * j) * 4);
+              y[4 * j] = rs.x + b4.x; y[4 * j + 1] = rs.y + b4.y; y[4 * j + 2] = rs.z + b4.z; y[4 * j + 3] = rs.w + b4.w;
+            }
+            if (c + 1 < c_end) load_resid(c0 + 32);          // next chunk's residual: in flight during the math below
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              y[j] += __uint_as_float(r[j]);
+              sum += y[j];
+              sq = fmaf(y[j], y[j], sq);
+              r[j] = __float_as_uint(y[j]);
+            }
+            tmem_st<32>(taddr + c0, r);
+            if (p.y_out != nullptr) {
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                sts_u4(xbuf + lane * 128 + ((j ^ (lane & 7)) << 4), make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
+              __syncwarp();
+              float* obase = p.y_out + wrow0 * p.N + n0 + c0;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + (lane >> 3), cc = lane & 7;
+                *reinterpret_cast<uint4*>(obase + static_cast<size_t>(rr) * p.N + cc * 4) = lds_u4(xbuf + rr * 128 + ((cc ^ (rr & 7)) << 4));
+              }
+            }
+          }
+          if (half == 1) {                                    // the 8 remainder columns (224..231) of the tile: direct
+            const int c0 = kFull * 32;
+            uint32_t r[32];
+            tmem_ld<8>(taddr + c0, r);
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float4 rs = __ldg(reinterpret_cast<const float4*>(p.resid + row * p.N + n0 + c0) + j);
+              const float4 b4 = lds_f4(sbias_addr + (n0 + c0 + 4 * j) * 4);
+              y[4 * j] = rs.x + b4.x; y[4 * j + 1] = rs.y + b4.y; y[4 * j + 2] = rs.z + b4.z; y[4 * j + 3] = rs.w + b4.w;
+            }
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              y[j] += __uint_as_float(r[j]);
+              sum += y[j];
+              sq = fmaf(y[j], y[j], sq);
+              r[j] = __float_as_uint(y[j]);
+            }
+            tmem_st<8>(taddr + c0, r);
+            if (p.y_out != nullptr) {
+              float4* dst = reinterpret_cast<float4*>(p.y_out + row * p.N + n0 + c0);
+              dst[0] = make_float4(y[0], y[1], y[2], y[3]);
+              dst[1] = make_float4(y[4], y[5], y[6], y[7]);
+            }
+          }
+        }
+        // ---------------- row statistics across the two column halves ----------------
+        sstat[half * kBM + row_in_tile] = make_float2(sum, sq);
+        tmem_wait_st();
+        named_bar_sync(1, kEpiThreads);
+        const float2 other = sstat[(half ^ 1) * kBM + row_in_tile];
+        const float mean = (sum + other.x) * (1.0f / (2 * BN_STORE));
+        const float var = fmaxf((sq + other.y) * (1.0f / (2 * BN_STORE)) - mean * mean, 0.0f);
+        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        // ---------------- phase B ----------------
+        for (int n_blk = 0; n_blk < 2; ++n_blk) {
+          const int n0 = n_blk * BN_STORE;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + n_blk * kAccStride;
+          auto norm4 = [&](const uint32_t* rr4, int col, float* o) {
+            const float4 g4 = lds_f4(sgamma_addr + col * 4), h4 = lds_f4(sbeta_addr + col * 4);
+            o[0] = (__uint_as_float(rr4[0]) - mean) * rstd * g4.x + h4.x;
+            o[1] = (__uint_as_float(rr4[1]) - mean) * rstd * g4.y + h4.y;
+            o[2] = (__uint_as_float(rr4[2]) - mean) * rstd * g4.z + h4.z;
+            o[3] = (__uint_as_float(rr4[3]) - mean) * rstd * g4.w + h4.w;
+          };
+#pragma unroll 1
+          for (int c = c_begin; c < c_end; ++c) {
+            const int c0 = c * 32;
+            uint32_t r[32];
+            tmem_ld<32>(taddr + c0, r);
+            tmem_wait_ld();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) norm4(r + 4 * j, n0 + c0 + 4 * j, v + 4 * j);
+            __syncwarp();
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+              sts_u4(xbuf + lane * 64 + ((cc ^ ((lane >> 1) & 3)) << 4),
+                     make_uint4(O::pack(v[8 * cc], v[8 * cc + 1]), O::pack(v[8 * cc + 2], v[8 * cc + 3]),
+                                O::pack(v[8 * cc + 4], v[8 * cc + 5]), O::pack(v[8 * cc + 6], v[8 * cc + 7])));
+            __syncwarp();
+            typename O::T* o16 = static_cast<typename O::T*>(p.out16) + wrow0 * p.N + n0 + c0;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + (lane >> 2), cc = lane & 3;
+              *reinterpret_cast<uint4*>(o16 + static_cast<size_t>(rr) * p.N + cc * 8) = lds_u4(xbuf + rr * 64 + ((cc ^ ((rr >> 1) & 3)) << 4));
+            }
+            if (p.out32 != nullptr) {
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                sts_u4(xbuf + lane * 128 + ((j ^ (lane & 7)) << 4),
+                       make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
+              __syncwarp();
+              float* o32 = p.out32 + wrow0 * p.N + n0 + c0;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + (lane >> 3), cc = lane & 7;
+                *reinterpret_cast<uint4*>(o32 + static_cast<size_t>(rr) * p.N + cc * 4) = lds_u4(xbuf + rr * 128 + ((cc ^ (rr & 7)) << 4));
+              }
+            }
+          }
+          if (half == 1) {
+            const int c0 = kFull * 32;
+            uint32_t r[32];
+            tmem_ld<8>(taddr + c0, r);
+            tmem_wait_ld();
+            float v[8];
+            norm4(r, n0 + c0, v);
+            norm4(r + 4, n0 + c0 + 4, v + 4);
+            *reinterpret_cast<uint4*>(static_cast<typename O::T*>(p.out16) + row * p.N + n0 + c0) =
+                make_uint4(O::pack(v[0], v[1]), O::pack(v[2], v[3]), O::pack(v[4], v[5]), O::pack(v[6], v[7]));
+            if (p.out32 != nullptr) {
+              float4* dst = reinterpret_cast<float4*>(p.out32 + row * p.N + n0 + c0);
+              dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+              dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[n_blk]), 0));   // release this accumulator
+        }
+        acc_phase ^= 1;
+      }
     }
   }
 

@@ -237,7 +237,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
   const int np = (n + 1) & ~1;            // layouts incl. the padding layout of an odd batch
   const int M = np * kBM;
   const int sms = h->num_sms & ~1;        // CTA pairs
-  auto pair_grid = [&](int n_tiles) { return std::min((np / 2) * n_tiles * 2, sms); };
+  auto pair_grid = [&](int) { return std::min(np, sms); };   // one CTA pair per 256-row block (it walks all N tiles of the block)
   int done = 0;
   // test tap: stop after `debug_stop_after` launches
 #define LDM_STAGE_DONE() do { if (h->debug_stop_after && ++done >= h->debug_stop_after) { CK(cudaGetLastError()); return LDM_OK; } } while (0)
@@ -260,15 +260,10 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       attention_kernel<BF16><<<np * h->desc.n_heads, kAttThreads, kAttSmemBytes, st>>>(h->qkv16, h->att16, h->S, d / h->desc.n_heads, h->desc.n_heads);
     }
     LDM_STAGE_DONE();
-    {  // out-projection (+bias) -> fp32
-      GemmParams p{M, d, d, d / kFF1Tile, h->bo[l], h->g32, d, 1.0f, 0};
+    {  // out-projection + bias + residual (from the NORMALISED x) -> y32 ; z16 = LayerNorm2(y)   [fused epilogue]
+      GemmParams p{M, d, d, d / kFF1Tile, h->bo[l], nullptr, d, 1.0f, 0, h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr, h->z16};
       ProfScope ps(h, CAT_OUTPROJ, st);
-      gemm_tc_kernel<kFF1Tile, 240, 5, EPI_F32, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 5>::kBytes, st>>>(h->m_att16, h->m_wo[l], p);
-    }
-    LDM_STAGE_DONE();
-    {  // y = g + x (residual from the NORMALISED x) ; z = LayerNorm2(y)
-      ProfScope ps(h, CAT_RESID_LN, st);
-      resid_ln_kernel<BF16><<<(M * 32 + 255) / 256, 256, 0, st>>>(h->g32, h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr, h->z16, M, d);
+      gemm_tc_kernel<kFF1Tile, 240, 5, EPI_LN, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<240, 5>::kBytes, st>>>(h->m_att16, h->m_wo[l], p);
     }
     LDM_STAGE_DONE();
     {  // FF1 + ReLU
@@ -277,20 +272,16 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 5>::kBytes, st>>>(h->m_z16, h->m_w1[l], p);
     }
     LDM_STAGE_DONE();
-    {  // FF2 (+bias) -> fp32
-      GemmParams p{M, d, ff, d / kFF1Tile, h->b2[l], h->g32, d, 1.0f, 0};
-      ProfScope ps(h, CAT_FF2, st);
-      gemm_tc_kernel<kFF1Tile, 240, 5, EPI_F32, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 5>::kBytes, st>>>(h->m_hid16, h->m_w2[l], p);
-    }
-    LDM_STAGE_DONE();
-    {  // h = g + y ; next block's AdaLN(h, t) (fp32 residual + 16-bit operand) or the head LayerNorm
-      ProfScope ps(h, CAT_RESID_LN, st);
+    {  // FF2 + bias + residual ; next block's AdaLN(h, t) (fp32 residual + 16-bit operand) or the head LayerNorm   [fused epilogue]
+      GemmParams p{M, d, ff, d / kFF1Tile, h->b2[l], nullptr, d, 1.0f, 0, h->y32, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
       if (l + 1 < L) {
         const float* tab = h->adaln + (static_cast<size_t>(l + 1) * T + t_model) * 2 * d;
-        resid_ln_kernel<BF16><<<(M * 32 + 255) / 256, 256, 0, st>>>(h->g32, h->y32, nullptr, tab, tab + d, 1, h->x32, h->x16, M, d);
+        p.ln_scale = tab; p.ln_shift = tab + d; p.adaln = 1; p.out32 = h->x32; p.out16 = h->x16;
       } else {
-        resid_ln_kernel<BF16><<<(M * 32 + 255) / 256, 256, 0, st>>>(h->g32, h->y32, nullptr, h->hlnw, h->hlnb, 0, nullptr, h->z16, M, d);
+        p.ln_scale = h->hlnw; p.ln_shift = h->hlnb; p.adaln = 0; p.out32 = nullptr; p.out16 = h->z16;
       }
+      ProfScope ps(h, CAT_FF2, st);
+      gemm_tc_kernel<kFF1Tile, 240, 5, EPI_LN, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<240, 5>::kBytes, st>>>(h->m_hid16, h->m_w2[l], p);
     }
     LDM_STAGE_DONE();
   }
@@ -467,13 +458,13 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
     TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, true>, GemmSmem<256, 5>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, true>, GemmSmem<240, 5>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, true>, GemmSmem<160, 5>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_F32, true>, GemmSmem<240, 5>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_LN, true>, GemmSmem<240, 5>::kBytes)));
     TRY((set_smem(attention_kernel<true>, kAttSmemBytes)));
   } else {
     TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, false>, GemmSmem<256, 5>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, false>, GemmSmem<240, 5>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, false>, GemmSmem<160, 5>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_F32, false>, GemmSmem<240, 5>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_LN, false>, GemmSmem<240, 5>::kBytes)));
     TRY((set_smem(attention_kernel<false>, kAttSmemBytes)));
   }
 #undef TRY

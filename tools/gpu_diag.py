@@ -94,12 +94,12 @@ def main():
             rec(stage=f"L{l}.qkv.pad_cols", max_abs=pad)
             stage += 1; run(stage)
             cmp(f"L{l}.attention", G.debug_read(eng, "att16", B)[:, :S], taps[f"att{l}"])
-            stage += 2; run(stage)      # out-proj GEMM + resid_ln
+            stage += 1; run(stage)      # out-proj GEMM with fused residual + LayerNorm2
             cmp(f"L{l}.outproj.y32", G.debug_read(eng, "y32", B)[:, :S], taps[f"y{l}"])
             cmp(f"L{l}.outproj.z16", G.debug_read(eng, "z16", B)[:, :S], taps[f"z{l}"])
             stage += 1; run(stage)
             cmp(f"L{l}.ff1.hid16", G.debug_read(eng, "hid16", B)[:, :S], taps[f"hid{l}"])
-            stage += 2; run(stage)      # FF2 GEMM + resid_ln
+            stage += 1; run(stage)      # FF2 GEMM with fused residual + AdaLN / head LN
             if l + 1 < spec.layers:
                 cmp(f"L{l}.ff2.x32", G.debug_read(eng, "x32", B)[:, :S], taps[f"x{l + 1}"])
             else:
