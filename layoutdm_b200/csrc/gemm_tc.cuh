@@ -301,6 +301,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const size_t row = static_cast<size_t>(m_blk) * kBM + row_in_tile;
         const size_t wrow0 = static_cast<size_t>(m_blk) * kBM + quad * 32;      // first row of this warp
         float sum = 0.0f, sq = 0.0f;
+        // pull this warp's residual rows (32 rows x 2 x 116/128 columns) from HBM into L2 while the MMAs run: the
+        // dependent loads of phase A then see L2 latency instead of DRAM latency
+        {
+          const int cols_per_tile = (c_end - c_begin) * 32;             // 128 (half 0) / 96 (half 1); remainder rides along
+          const int lines_per_row = (cols_per_tile * 4 + 127) / 128 + (half == 1 ? 1 : 0);
+          for (int i = lane; i < 2 * 32 * lines_per_row; i += 32) {
+            const int t = i / (32 * lines_per_row), rem = i % (32 * lines_per_row);
+            const int rr = rem / lines_per_row, ln = rem % lines_per_row;
+            const float* a = p.resid + (wrow0 + rr) * p.N + t * BN_STORE + c_begin * 32 + ln * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+          }
+        }
         // ---------------- phase A ----------------
         for (int n_blk = 0; n_blk < 2; ++n_blk) {
           const int n0 = n_blk * BN_STORE;
