@@ -75,6 +75,15 @@ LDM_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* ba
       : "memory");
 }
 
+// TMA store of a staged tile (shared -> global), tracked by the issuing thread's bulk async-group
+LDM_DEVINL void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+LDM_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+LDM_DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // staged sources reusable
+LDM_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }          // stores complete
+
 // multicast variant: the tile lands at the same smem offset (and signals the same-offset mbarrier) in every CTA of `mask`
 LDM_DEVINL void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, uint16_t mask) {
   asm volatile(

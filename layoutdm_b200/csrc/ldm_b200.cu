@@ -68,6 +68,23 @@ int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uin
   return LDM_OK;
 }
 
+// 32 x 32-element block of a row-major [rows][cols] tensor as the GEMM epilogue stages it: 16-bit -> 64-byte rows
+// (64B swizzle), fp32 -> 128-byte rows (128B swizzle)
+int make_block_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, int elem_bytes, bool bf16) {
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * elem_bytes};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                 : (bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+  CUresult r = g_encode(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        elem_bytes == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LDM_ERR_CUDA, "cuTensorMapEncodeTiled (block map) failed (%d) rows=%llu cols=%llu", (int)r,
+                                     (unsigned long long)rows, (unsigned long long)cols);
+  return LDM_OK;
+}
+
 // (B,S,C) contiguous <-> padded internal logits [B*128][160]
 __global__ void logits_scatter_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_layouts, int S, int C) {
   const size_t n = static_cast<size_t>(n_layouts) * S * C;
@@ -112,7 +129,8 @@ struct LdmHandle {
   long long* ids[2] = {nullptr, nullptr};
   long long* ids_final = nullptr;
   long long *c_seq = nullptr, *c_seq_orig = nullptr; unsigned char* c_mask = nullptr; float* c_tbl = nullptr;  // staging for ldm_sample_host
-  CUtensorMap m_x16, m_att16, m_z16, m_hid16;
+  CUtensorMap m_x16, m_att16, m_z16, m_hid16;                       // A operands (128 x 64 boxes)
+  CUtensorMap b_qkv16, b_hid16, b_z16, b_x16, b_x32, b_y32, b_logits;  // epilogue 32 x 32 blocks
   std::vector<void*> owned;
 };
 
@@ -228,6 +246,13 @@ int ensure_workspace(LdmHandle* h, int n_layouts) {
   if ((rc = make_map(&h->m_att16, h->att16, M, d, kBM, h->bf16))) return rc;
   if ((rc = make_map(&h->m_z16, h->z16, M, d, kBM, h->bf16))) return rc;
   if ((rc = make_map(&h->m_hid16, h->hid16, M, ff, kBM, h->bf16))) return rc;
+  if ((rc = make_block_map(&h->b_qkv16, h->qkv16, M, kQkvN, 2, h->bf16))) return rc;
+  if ((rc = make_block_map(&h->b_hid16, h->hid16, M, ff, 2, h->bf16))) return rc;
+  if ((rc = make_block_map(&h->b_z16, h->z16, M, d, 2, h->bf16))) return rc;
+  if ((rc = make_block_map(&h->b_x16, h->x16, M, d, 2, h->bf16))) return rc;
+  if ((rc = make_block_map(&h->b_x32, h->x32, M, d, 4, false))) return rc;
+  if ((rc = make_block_map(&h->b_y32, h->y32, M, d, 4, false))) return rc;
+  if ((rc = make_block_map(&h->b_logits, h->logits, M, kLogitLd, 4, false))) return rc;
   return LDM_OK;
 }
 
@@ -252,7 +277,8 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     {  // QKV projection (+bias, q * 1/sqrt(head_dim))
       GemmParams p{M, kQkvN, d, kQkvN / 256, h->bqkv[l], h->qkv16, kQkvN, 1.0f / sqrtf(static_cast<float>(d / h->desc.n_heads)), 8 * kHeadPad};
       ProfScope ps(h, CAT_QKV, st);
-      gemm_tc_kernel<256, 256, 5, EPI_QKV, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 5>::kBytes, st>>>(h->m_x16, h->m_wqkv[l], p);
+      gemm_tc_kernel<256, 256, 5, EPI_QKV, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 5, EPI_QKV>::kBytes, st>>>(
+          h->m_x16, h->m_wqkv[l], h->b_qkv16, h->b_qkv16, h->b_qkv16, h->b_qkv16, p);
     }
     LDM_STAGE_DONE();
     {
@@ -261,34 +287,39 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     }
     LDM_STAGE_DONE();
     {  // out-projection + bias + residual (from the NORMALISED x) -> y32 ; z16 = LayerNorm2(y)   [fused epilogue]
-      GemmParams p{M, d, d, d / kFF1Tile, h->bo[l], nullptr, d, 1.0f, 0, h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr, h->z16};
+      GemmParams p{M, d, d, d / kFF1Tile, h->bo[l], h->z16, d, 1.0f, 0, h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr};
       ProfScope ps(h, CAT_OUTPROJ, st);
-      gemm_tc_kernel<kFF1Tile, 240, 5, EPI_LN, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<240, 5>::kBytes, st>>>(h->m_att16, h->m_wo[l], p);
+      gemm_tc_kernel<kFF1Tile, 240, 4, EPI_LN, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<240, 4, EPI_LN>::kBytes, st>>>(
+          h->m_att16, h->m_wo[l], h->b_z16, h->b_x32, h->b_y32, h->b_y32, p);
     }
     LDM_STAGE_DONE();
     {  // FF1 + ReLU
       GemmParams p{M, ff, d, ff / kFF1Tile, h->b1[l], h->hid16, ff, 1.0f, 0};
       ProfScope ps(h, CAT_FF1, st);
-      gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 5>::kBytes, st>>>(h->m_z16, h->m_w1[l], p);
+      gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 5, EPI_RELU>::kBytes, st>>>(
+          h->m_z16, h->m_w1[l], h->b_hid16, h->b_hid16, h->b_hid16, h->b_hid16, p);
     }
     LDM_STAGE_DONE();
     {  // FF2 + bias + residual ; next block's AdaLN(h, t) (fp32 residual + 16-bit operand) or the head LayerNorm   [fused epilogue]
-      GemmParams p{M, d, ff, d / kFF1Tile, h->b2[l], nullptr, d, 1.0f, 0, h->y32, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
+      GemmParams p{M, d, ff, d / kFF1Tile, h->b2[l], nullptr, d, 1.0f, 0, h->y32, nullptr, nullptr, nullptr, 0, nullptr};
+      const CUtensorMap* mo = &h->b_z16;
       if (l + 1 < L) {
         const float* tab = h->adaln + (static_cast<size_t>(l + 1) * T + t_model) * 2 * d;
-        p.ln_scale = tab; p.ln_shift = tab + d; p.adaln = 1; p.out32 = h->x32; p.out16 = h->x16;
+        p.ln_scale = tab; p.ln_shift = tab + d; p.adaln = 1; p.out32 = h->x32; p.out = h->x16; mo = &h->b_x16;
       } else {
-        p.ln_scale = h->hlnw; p.ln_shift = h->hlnb; p.adaln = 0; p.out32 = nullptr; p.out16 = h->z16;
+        p.ln_scale = h->hlnw; p.ln_shift = h->hlnb; p.adaln = 0; p.out32 = nullptr; p.out = h->z16;
       }
       ProfScope ps(h, CAT_FF2, st);
-      gemm_tc_kernel<kFF1Tile, 240, 5, EPI_LN, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<240, 5>::kBytes, st>>>(h->m_hid16, h->m_w2[l], p);
+      gemm_tc_kernel<kFF1Tile, 240, 4, EPI_LN, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<240, 4, EPI_LN>::kBytes, st>>>(
+          h->m_hid16, h->m_w2[l], *mo, h->b_y32, h->b_x32, h->b_x32, p);
     }
     LDM_STAGE_DONE();
   }
   {  // vocabulary head -> fp32 logits
     GemmParams p{M, kLogitLd, d, 1, nullptr, h->logits, kLogitLd, 1.0f, 0};
     ProfScope ps(h, CAT_HEAD, st);
-    gemm_tc_kernel<160, 160, 5, EPI_F32, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<160, 5>::kBytes, st>>>(h->m_z16, h->m_whead, p);
+    gemm_tc_kernel<160, 160, 5, EPI_F32, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<160, 5, EPI_F32>::kBytes, st>>>(
+        h->m_z16, h->m_whead, h->b_logits, h->b_logits, h->b_logits, h->b_logits, p);
   }
 #undef LDM_STAGE_DONE
   CK(cudaGetLastError());
@@ -455,16 +486,16 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   if (cudaDeviceSynchronize() != cudaSuccess) { ldm_destroy(h); return fail(LDM_ERR_CUDA, "weight packing failed: %s", cudaGetErrorString(cudaGetLastError())); }
 
   if (h->bf16) {
-    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, true>, GemmSmem<256, 5>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, true>, GemmSmem<240, 5>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, true>, GemmSmem<160, 5>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_LN, true>, GemmSmem<240, 5>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, true>, GemmSmem<256, 5, EPI_QKV>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, true>, GemmSmem<240, 5, EPI_RELU>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, true>, GemmSmem<160, 5, EPI_F32>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 4, EPI_LN, true>, GemmSmem<240, 4, EPI_LN>::kBytes)));
     TRY((set_smem(attention_kernel<true>, kAttSmemBytes)));
   } else {
-    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, false>, GemmSmem<256, 5>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, false>, GemmSmem<240, 5>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, false>, GemmSmem<160, 5>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_LN, false>, GemmSmem<240, 5>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, false>, GemmSmem<256, 5, EPI_QKV>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, false>, GemmSmem<240, 5, EPI_RELU>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, false>, GemmSmem<160, 5, EPI_F32>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 4, EPI_LN, false>, GemmSmem<240, 4, EPI_LN>::kBytes)));
     TRY((set_smem(attention_kernel<false>, kAttSmemBytes)));
   }
 #undef TRY
