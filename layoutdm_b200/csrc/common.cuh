@@ -82,11 +82,6 @@ LDM_DEVINL void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int32_t 
 }
 LDM_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 LDM_DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // staged sources reusable
-LDM_DEVINL void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }   // all but the newest group
-// pull a tensor block from HBM into L2 (no smem destination): used to hide DRAM latency of loads issued later
-LDM_DEVINL void tma_prefetch_l2_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
-}
 LDM_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }          // stores complete
 
 // multicast variant: the tile lands at the same smem offset (and signals the same-offset mbarrier) in every CTA of `mask`

@@ -192,7 +192,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t sbias_addr = smem_u32(sbias);
     const uint32_t wbuf = smem_u32(smem + SM::kOffStaging) + we * SM::kWarpStage;
     const uint32_t s32 = wbuf;                                              // fp32 store block, rows of 128 B
-    const uint32_t s16_base = EPI == EPI_LN ? wbuf + 4096 : wbuf;           // 16-bit store block(s), rows of 64 B
+    const uint32_t s16 = EPI == EPI_LN ? wbuf + 4096 : wbuf;                // 16-bit store block, rows of 64 B
     const int c_begin = half == 0 ? 0 : kSplit, c_end = half == 0 ? kSplit : kFull;
     const uint32_t tlane = static_cast<uint32_t>(quad * 32) << 16;
 
@@ -208,15 +208,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) { tma_store_2d(m, s32, col, row0); bulk_commit(); }
     };
-    uint32_t s16_flip = 0;                     // non-LN: two 2-KB 16-bit blocks alternate inside the 4-KB staging area
     auto store_16 = [&](const CUtensorMap* m, const float* v, int col, int row0) {
-      uint32_t s16 = s16_base;
-      if constexpr (EPI != EPI_LN) {
-        s16 += s16_flip; s16_flip ^= 2048;
-        if (lane == 0) bulk_wait_read1();      // the store issued two blocks ago has released this buffer
-      } else {
-        if (lane == 0) bulk_wait_read0();
-      }
+      if (lane == 0) bulk_wait_read0();
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -310,17 +303,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const size_t row = static_cast<size_t>(m_blk) * kBM + row_in_tile;
         const int wrow0 = m_blk * kBM + quad * 32;            // first row of this warp
         float sum = 0.0f, sq = 0.0f;
-        // pull the NEXT row block's residual (this warp's 32 rows, its columns of both tiles) from HBM into L2 now, so the
-        // dependent TMA loads of its phase A see L2 latency; the very first block is prefetched before the loop
-        auto prefetch_resid = [&](int sup2) {
-          if (lane == 0 && sup2 < n_super) {
-            const int r0 = (2 * sup2 + static_cast<int>(cta_rank)) * kBM + quad * 32;
-            for (int t = 0; t < 2; ++t)
-              for (int c = c_begin; c < c_end + (half == 1 ? 1 : 0); ++c) tma_prefetch_l2_2d(&map_resid, t * BN_STORE + c * 32, r0);
-          }
-        };
-        if (sup == pair) prefetch_resid(sup);
-        prefetch_resid(sup + n_pairs);
         // ---------------- phase A ----------------
         for (int n_blk = 0; n_blk < 2; ++n_blk) {
           const int n0 = n_blk * BN_STORE;
