@@ -283,7 +283,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     LDM_STAGE_DONE();
     {
       ProfScope ps(h, CAT_ATTN, st);
-      attention_kernel<BF16><<<np * h->desc.n_heads, kAttThreads, kAttSmemBytes, st>>>(h->qkv16, h->att16, h->S, d / h->desc.n_heads, h->desc.n_heads);
+      attention_kernel<BF16><<<np * (h->desc.n_heads / kAttHeadsPerCta), kAttThreads, kAttSmemBytes, st>>>(h->qkv16, h->att16, h->S, d / h->desc.n_heads, h->desc.n_heads);
     }
     LDM_STAGE_DONE();
     {  // out-projection + bias + residual (from the NORMALISED x) -> y32 ; z16 = LayerNorm2(y)   [fused epilogue]
