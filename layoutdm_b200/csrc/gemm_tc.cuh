@@ -52,6 +52,7 @@ struct GemmParams {
   const float* ln_shift;  // [N]
   int adaln;
   float* out32;           // fp32 [M][N] normalised output (next residual, AdaLN case) or nullptr
+  int dbg;                // bring-up probe (env LDM_GEMM_DEBUG): 1 = skip the MMAs, 2 = skip the TMA operand loads; results are garbage
 };
 
 template <int UMMA_N, int STAGES, int EPI>
@@ -149,9 +150,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * SM::kStageBytes;
           const uint32_t lead_full = mapa_shared(smem_u32(&full[stage]), 0);
+          if (p.dbg == 2) { mbar_arrive_cluster(lead_full); }
+          else {
           mbar_arrive_expect_tx_cluster(lead_full, SM::kStageBytes);
           tma_load_2d_2cta(sa, &map_a, lead_full, kb * kBK, m_blk * kBM);
           tma_load_2d_2cta(sa + kATileBytes, &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * kHalfRows);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -174,6 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint64_t da = make_smem_desc_sw128(sa);
           const uint64_t db = make_smem_desc_sw128(sa + kATileBytes);
           const int nk = min(kBK, p.K - kb * kBK) / kUmmaK;     // K tail: TMA zero-fills, skip the zero k-steps
+          if (p.dbg != 1)
           for (int k = 0; k < nk; ++k)
             umma_f16_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);   // +32 B per k-step (>>4 = 2)
           umma_commit_2cta_mc(&empty[stage], static_cast<uint16_t>(0b11));       // free the stage in both CTAs

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 #include <vector>
@@ -112,6 +113,7 @@ struct LdmHandle {
   bool bf16 = false;
   int num_sms = 148;
   int64_t launches = 0;
+  int gemm_dbg = 0;           // env LDM_GEMM_DEBUG (bring-up probe, see GemmParams::dbg)
   int debug_stop_after = 0;   // test tap: stop the denoiser after this many launches (0 = run everything)
   bool prof = false;          // per-kernel CUDA-event timing (ldm_profile_begin/end)
   struct ProfRec { int cat; cudaEvent_t a, b; };
@@ -276,6 +278,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
   for (int l = 0; l < L; ++l) {
     {  // QKV projection (+bias, q * 1/sqrt(head_dim))
       GemmParams p{M, kQkvN, d, kQkvN / 256, h->bqkv[l], h->qkv16, kQkvN, 1.0f / sqrtf(static_cast<float>(d / h->desc.n_heads)), 8 * kHeadPad};
+      p.dbg = h->gemm_dbg;
       ProfScope ps(h, CAT_QKV, st);
       gemm_tc_kernel<256, 256, 5, EPI_QKV, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 5, EPI_QKV>::kBytes, st>>>(
           h->m_x16, h->m_wqkv[l], h->b_qkv16, h->b_qkv16, h->b_qkv16, h->b_qkv16, p);
@@ -288,6 +291,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     LDM_STAGE_DONE();
     {  // out-projection + bias + residual (from the NORMALISED x) -> y32 ; z16 = LayerNorm2(y)   [fused epilogue]
       GemmParams p{M, d, d, d / kFF1Tile, h->bo[l], h->z16, d, 1.0f, 0, h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr};
+      p.dbg = h->gemm_dbg;
       ProfScope ps(h, CAT_OUTPROJ, st);
       gemm_tc_kernel<kFF1Tile, 240, 4, EPI_LN, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<240, 4, EPI_LN>::kBytes, st>>>(
           h->m_att16, h->m_wo[l], h->b_z16, h->b_x32, h->b_y32, h->b_y32, p);
@@ -295,6 +299,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     LDM_STAGE_DONE();
     {  // FF1 + ReLU
       GemmParams p{M, ff, d, ff / kFF1Tile, h->b1[l], h->hid16, ff, 1.0f, 0};
+      p.dbg = h->gemm_dbg;
       ProfScope ps(h, CAT_FF1, st);
       gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 5, EPI_RELU>::kBytes, st>>>(
           h->m_z16, h->m_w1[l], h->b_hid16, h->b_hid16, h->b_hid16, h->b_hid16, p);
@@ -309,6 +314,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       } else {
         p.ln_scale = h->hlnw; p.ln_shift = h->hlnb; p.adaln = 0; p.out32 = nullptr; p.out = h->z16;
       }
+      p.dbg = h->gemm_dbg;
       ProfScope ps(h, CAT_FF2, st);
       gemm_tc_kernel<kFF1Tile, 240, 4, EPI_LN, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<240, 4, EPI_LN>::kBytes, st>>>(
           h->m_hid16, h->m_w2[l], *mo, h->b_y32, h->b_x32, h->b_x32, p);
@@ -414,6 +420,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   h->desc = *desc; h->C = C; h->S = S; h->L = L; h->T = T; h->bf16 = desc->operand_dtype == 1;
   h->G = desc->q_type == 0 ? desc->n_attr : 1;
   h->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("LDM_GEMM_DEBUG")) h->gemm_dbg = atoi(e);
 #define TRY(x) do { rc = (x); if (rc) { ldm_destroy(h); return rc; } } while (0)
 
   TRY(dev_upload(h, &h->cat_emb, w->cat_emb, static_cast<size_t>(C) * d));
