@@ -150,7 +150,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * SM::kStageBytes;
           const uint32_t lead_full = mapa_shared(smem_u32(&full[stage]), 0);
-          if (p.dbg == 2) { mbar_arrive_cluster(lead_full); }
+          if (p.dbg >= 2) { mbar_arrive_cluster(lead_full); }
           else {
           mbar_arrive_expect_tx_cluster(lead_full, SM::kStageBytes);
           tma_load_2d_2cta(sa, &map_a, lead_full, kb * kBK, m_blk * kBM);
@@ -239,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_after();
         const uint32_t taddr = tmem_base + tlane + acc * kAccStride;
 #pragma unroll 1
-        for (int c = c_begin; c < c_end; ++c) {
+        for (int c = c_begin; c < (p.dbg == 3 ? c_begin : c_end); ++c) {
           const int c0 = c * 32;
           uint32_t r[32];
           tmem_ld<32>(taddr + c0, r);
