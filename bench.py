@@ -153,6 +153,8 @@ def cpu_sample_plan(budget_s, orc, O):
 def run_reference_arm(args, world, rank):
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for its workers: the CPU arm uses every host core it can get
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
     orc, O = make_cpu_oracle()
     cores = torch.get_num_threads()
     total_budget = 150.0
