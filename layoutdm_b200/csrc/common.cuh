@@ -82,7 +82,6 @@ LDM_DEVINL void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int32_t 
 }
 LDM_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 LDM_DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // staged sources reusable
-LDM_DEVINL void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }   // all but the newest group
 LDM_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }          // stores complete
 
 // multicast variant: the tile lands at the same smem offset (and signals the same-offset mbarrier) in every CTA of `mask`

@@ -61,8 +61,8 @@ struct GemmSmem {
   static constexpr int kStageBytes = kATileBytes + kBHalfBytes;
   static_assert(kBHalfBytes % 1024 == 0, "half weight tile must keep 1024-B (swizzle atom) alignment");
   // per-epilogue-warp staging: [0,4K) 32x32 fp32 store block (128B swizzle) / 16-bit store block (64B swizzle);
-  // LN: [4K,8K) + [8K,12K) two residual load blocks (128B swizzle, loads run two blocks ahead), [12K,14K) 16-bit store block
-  static constexpr int kWarpStage = EPI == EPI_LN ? 14336 : 4096;
+  // LN: [4K,6K) 16-bit store block, [6K,10K) residual load block (128B swizzle)
+  static constexpr int kWarpStage = EPI == EPI_LN ? 10240 : 4096;
   static constexpr int kStagingBytes = 8 * kWarpStage;
   static constexpr int kBarBytes = 256;
   static constexpr int kBiasBytes = 1856 * 4;   // bias (and, for LN, gamma / beta) vectors of the layer
@@ -105,10 +105,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* empty = bars + STAGES;           // per CTA: released by the leader's multicast tcgen05.commit
   uint64_t* tfull = bars + 2 * STAGES;       // per CTA: accumulator ready (multicast commit)
   uint64_t* tempty = bars + 2 * STAGES + 2;  // leader's copy: 16 warp arrivals (8 epilogue warps x 2 CTAs)
-  uint64_t* lbars = bars + 2 * STAGES + 4;   // LN: two residual-load barriers per epilogue warp
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 20);
+  uint64_t* lbars = bars + 2 * STAGES + 4;   // LN: one residual-load barrier per epilogue warp
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
   float* sbias = reinterpret_cast<float*>(smem + SM::kOffBias);
-  static_assert((2 * STAGES + 20) * 8 + 4 <= SM::kBarBytes, "barrier block overflow");
+  static_assert((2 * STAGES + 12) * 8 + 4 <= SM::kBarBytes, "barrier block overflow");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + kBK - 1) / kBK;
@@ -129,7 +129,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tma_prefetch_desc(&map_out);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }
-    for (int i = 0; i < 16; ++i) mbar_init(&lbars[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&lbars[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2cta(tmem_ptr, kTmemCols);
@@ -197,14 +197,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t sbias_addr = smem_u32(sbias);
     const uint32_t wbuf = smem_u32(smem + SM::kOffStaging) + we * SM::kWarpStage;
     const uint32_t s32 = wbuf;                                              // fp32 store block, rows of 128 B
-    const uint32_t s16 = EPI == EPI_LN ? wbuf + 12288 : wbuf;               // 16-bit store block, rows of 64 B
+    const uint32_t s16 = EPI == EPI_LN ? wbuf + 4096 : wbuf;                // 16-bit store block, rows of 64 B
     const int c_begin = half == 0 ? 0 : kSplit, c_end = half == 0 ? kSplit : kFull;
     const uint32_t tlane = static_cast<uint32_t>(quad * 32) << 16;
 
     // stage one 32 x 32 block (this warp's rows, 32 columns) and hand it to the TMA engine
-    // `alt`: the previous store used the OTHER staging buffer, so only the stores before it must have drained
-    auto store_f32 = [&](const CUtensorMap* m, const float* v, int col, int row0, bool alt = false) {
-      if (lane == 0) { if (alt) bulk_wait_read1(); else bulk_wait_read0(); }   // staging buffer free again
+    auto store_f32 = [&](const CUtensorMap* m, const float* v, int col, int row0) {
+      if (lane == 0) bulk_wait_read0();        // earlier stores have finished reading the staging buffers
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -214,8 +213,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) { tma_store_2d(m, s32, col, row0); bulk_commit(); }
     };
-    auto store_16 = [&](const CUtensorMap* m, const float* v, int col, int row0, bool alt = false) {
-      if (lane == 0) { if (alt) bulk_wait_read1(); else bulk_wait_read0(); }
+    auto store_16 = [&](const CUtensorMap* m, const float* v, int col, int row0) {
+      if (lane == 0) bulk_wait_read0();
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -300,10 +299,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // One CTA owns 128 complete rows: both 232-column tiles of its row block run back to back on this pair.
       float2* sstat = reinterpret_cast<float2*>(smem + SM::kOffStat);
       const uint32_t sgamma_addr = sbias_addr + p.N * 4, sbeta_addr = sbias_addr + 2 * p.N * 4;
-      const uint32_t lbuf = wbuf + 4096;                     // two residual blocks, rows of 128 B (128B swizzle)
-      uint8_t* lbuf_ptr = smem + SM::kOffStaging + we * SM::kWarpStage + 4096;
-      uint64_t* lbar = &lbars[2 * we];
-      uint32_t lphase[2] = {0, 0};
+      const uint32_t lbuf = wbuf + 6144;                     // residual block, rows of 128 B (128B swizzle)
+      uint8_t* lbuf_ptr = smem + SM::kOffStaging + we * SM::kWarpStage + 6144;
+      uint64_t* lbar = &lbars[we];
+      uint32_t lphase = 0;
       for (int sup = pair; sup < n_super; sup += n_pairs) {
         const int m_blk = 2 * sup + static_cast<int>(cta_rank);
         const size_t row = static_cast<size_t>(m_blk) * kBM + row_in_tile;
@@ -313,15 +312,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int n_blk = 0; n_blk < 2; ++n_blk) {
           const int n0 = n_blk * BN_STORE;
           const uint32_t taddr = tmem_base + tlane + n_blk * kAccStride;
-          auto issue_resid = [&](int c) {                     // async: 32 rows x 32 fp32 of the residual -> lbuf[(c - c_begin) & 1]
+          auto issue_resid = [&](int c0) {                    // async: 32 rows x 32 fp32 of the residual -> lbuf
             if (lane == 0) {
-              const int b = (c - c_begin) & 1;
-              mbar_arrive_expect_tx(&lbar[b], 4096);
-              tma_load_2d(lbuf_ptr + b * 4096, &map_resid, &lbar[b], n0 + c * 32, wrow0);
+              mbar_arrive_expect_tx(lbar, 4096);
+              tma_load_2d(lbuf_ptr, &map_resid, lbar, n0 + c0, wrow0);
             }
           };
-          issue_resid(c_begin);                               // two blocks in flight while the MMAs of this tile still run
-          if (c_begin + 1 < c_end) issue_resid(c_begin + 1);
+          issue_resid(c_begin * 32);                          // in flight while the MMAs of this tile still run
           float rem_res[8];
           if (half == 1) {                                    // remainder columns 224..231: direct (also early)
 #pragma unroll
@@ -337,17 +334,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int c0 = c * 32;
             uint32_t r[32];
             tmem_ld<32>(taddr + c0, r);
-            const int lb = (c - c_begin) & 1;
-            mbar_wait(&lbar[lb], lphase[lb]); lphase[lb] ^= 1;   // residual block has landed
+            mbar_wait(lbar, lphase); lphase ^= 1;             // residual block has landed
             float y[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 rs = lds_f4(lbuf + lb * 4096 + lane * 128 + ((j ^ (lane & 7)) << 4));
+              const float4 rs = lds_f4(lbuf + lane * 128 + ((j ^ (lane & 7)) << 4));
               const float4 b4 = lds_f4(sbias_addr + (n0 + c0 + 4 * j) * 4);
               y[4 * j] = rs.x + b4.x; y[4 * j + 1] = rs.y + b4.y; y[4 * j + 2] = rs.z + b4.z; y[4 * j + 3] = rs.w + b4.w;
             }
             __syncwarp();                                     // every lane is done reading lbuf
-            if (c + 2 < c_end) issue_resid(c + 2);            // refill this buffer: loads stay two blocks ahead
+            if (c + 1 < c_end) issue_resid(c0 + 32);          // next block streams in during the math / stores below
             tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -414,8 +410,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float v[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) norm4(r + 4 * j, n0 + c0 + 4 * j, v + 4 * j);
-            store_16(&map_out, v, n0 + c0, wrow0, p.out32 != nullptr);   // with out32 the stores alternate s16 / s32
-            if (p.out32 != nullptr) store_f32(&map_out32, v, n0 + c0, wrow0, true);
+            store_16(&map_out, v, n0 + c0, wrow0);
+            if (p.out32 != nullptr) store_f32(&map_out32, v, n0 + c0, wrow0);
           }
           if (half == 1) {
             const int c0 = kFull * 32;
