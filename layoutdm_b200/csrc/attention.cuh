@@ -1,183 +1,203 @@
-// Per-(layout, head) self-attention of the LayoutDM denoiser: O = softmax(Q K^T) V, S = 125 keys, head_dim 58.
+// Per-(layout, head) self-attention of the LayoutDM denoiser on tcgen05: O = softmax(Q K^T) V, 125 keys, head_dim 58.
 // (nn.MultiheadAttention inside Block._sa_block, T/models/transformer_utils.py:140-142,191-205; no masks.)
 //
 // Input  qkv [M][1536] 16-bit, per-head column blocks padded 58 -> 64 with zeros:
 //        Q_h = cols [h*64, h*64+64), K_h = 512 + ..., V_h = 1024 + ... ; Q is already scaled by 1/sqrt(58).
-// Output att [M][464] 16-bit, heads concatenated compactly (col = h*58 + j) = A operand of the out-projection.
+// Output att [M][512] 16-bit, head h in cols [h*64, h*64+64) (cols 58..63 of every head are exact zeros; the out-projection
+//        weight is packed with matching zero columns) = A operand of the out-projection.
 //
-// One CTA = 4 heads of one layout, head after head (the next head's Q/K/V tiles stream in through cp.async while the
-// current one is computed); per head: 128 query rows (125 valid) x 128 keys (125 valid, the rest masked to -inf).
-// 8 warps x 16 query rows; the whole score row lives in registers, so the softmax is exact (max, exp, sum,
-// normalise) before the probabilities are rounded to the operand dtype -- the same rounding points as the
-// oracle's same-rounding mode.  Contractions use warp-level mma.sync m16n8k16 (fp32 accumulate): attention
-// is 1.07 % of the denoiser FLOPs; the 98.9 % in the linear layers run on tcgen05.
+// One CTA = 4 heads of one layout (128 query rows x 128 keys per head), 160 threads, two CTAs per SM:
+//   warp 0 (one thread) : TMA loads of the Q / K / V head tiles (128B swizzle) and all tcgen05.mma issue:
+//                           S[128x128] = Q K^T      A = Q (K-major), B = K (K-major), 4 MMAs of k=16, fp32 in TMEM cols 0..127
+//                           O[128x64]  = P V        A = P (K-major, written by the softmax warps), B = V as loaded
+//                                                   ([key][d] rows = MN-major operand), 8 MMAs of k=16, TMEM cols 128..191
+//   warps 1..4          : thread = query row.  Exact softmax from TMEM (max pass, then exp2 / sum in registers), the
+//                         normalised probabilities are rounded to the operand dtype and written as the P operand tile;
+//                         later O is read back from TMEM, packed and TMA-stored.
+// The next head's Q/K tiles are requested as soon as the S MMAs have retired, the next V once the PV MMAs have retired, so
+// the loads overlap the softmax; the second CTA on the SM fills the remaining bubbles.
 #pragma once
 #include "common.cuh"
 
 namespace ldm {
 
-constexpr int kAttThreads = 256;
-constexpr int kAttHeadsPerCta = 4;               // a CTA walks 4 heads of one layout with double-buffered staging
-constexpr int kAttTileBytes = 3 * 128 * 128;     // Q, K, V tiles of one head: 128 rows x 64 x 2 B each
-constexpr int kAttSmemBytes = 2 * kAttTileBytes; // two heads in flight
+constexpr int kAttThreads = 160;
+constexpr int kAttHeadsPerCta = 4;
+constexpr int kAttTile = 128 * 128;                 // one 128 x 64 16-bit tile = 16 KB
+// smem: Q | K | V | P (2 k-blocks) | O staging | barriers
+constexpr int kAttOffQ = 0, kAttOffK = kAttTile, kAttOffV = 2 * kAttTile, kAttOffP = 3 * kAttTile, kAttOffO = 5 * kAttTile;
+constexpr int kAttOffBar = 6 * kAttTile;
+constexpr int kAttSmemBytes = 6 * kAttTile + 128 + 1024;   // + barriers + alignment slack
+constexpr uint32_t kAttTmemCols = 256;              // S: cols 0..127, O: cols 128..191
 
-template <bool BF16>
-LDM_DEVINL void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  if constexpr (BF16) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-  } else {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-  }
+// MN-major (rows = K index, 64 contiguous 16-bit elements = N) operand tile with 128-byte swizzle, 8-row groups 1024 B apart
+LDM_DEVINL uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;               // LBO: single 64-element atom along N, unused
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;       // SBO: stride between groups of 8 K-rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
 }
-LDM_DEVINL void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-LDM_DEVINL void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-// byte offset of 16-byte chunk `c` (0..7) of row `r` in a [128][64 x 16-bit] tile, XOR-swizzled so that the
-// eight rows an ldmatrix phase touches fall into distinct banks
-LDM_DEVINL uint32_t att_off(int r, int c) { return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4)); }
 
 template <bool BF16>
 __global__ void __launch_bounds__(kAttThreads, 2)
-attention_kernel(const void* __restrict__ qkv_, void* __restrict__ att_, int n_valid /*125*/, int head_dim /*58*/, int n_heads /*8*/) {
+attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64 x 128*/,
+                 const __grid_constant__ CUtensorMap map_att /*[M][512], box 64 x 128*/, int n_valid /*125*/, int n_heads /*8*/) {
   using O = OpT<BF16>;
-  using T = typename O::T;
-  extern __shared__ __align__(128) uint8_t att_smem[];
-  const T* qkv = static_cast<const T*>(qkv_);
-  T* att = static_cast<T*>(att_);
+  extern __shared__ uint8_t att_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAttOffBar);
+  uint64_t* qk_full = bars + 0;   // tx: Q + K tiles
+  uint64_t* v_full = bars + 1;    // tx: V tile
+  uint64_t* s_full = bars + 2;    // commit: S ready (and Q, K smem free)
+  uint64_t* p_ready = bars + 3;   // 128 arrivals: P tile written, S consumed
+  uint64_t* o_full = bars + 4;    // commit: O ready (and P, V smem free)
+  uint64_t* o_done = bars + 5;    // 128 arrivals: O consumed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int groups = n_heads / kAttHeadsPerCta;
   const int layout = blockIdx.x / groups, h0 = (blockIdx.x % groups) * kAttHeadsPerCta;
-  const int ldq = 3 * n_heads * 64;
-  const size_t row0 = static_cast<size_t>(layout) * 128;
-  const uint32_t sbase = smem_u32(att_smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int m0 = warp * 16;
-  const int ldo = n_heads * head_dim;
+  const int row0 = layout * 128;
 
-  // stage the Q, K, V tiles of head h into buffer `buf` (cp.async, 16 B per thread per op)
-  auto stage = [&](int h, int buf) {
-    for (int i = threadIdx.x; i < 3 * 128 * 8; i += kAttThreads) {
-      const int mat = i / (128 * 8), r = (i / 8) % 128, c = i % 8;
-      const T* src = qkv + (row0 + r) * ldq + mat * (n_heads * 64) + h * 64 + c * 8;
-      const uint32_t dst = sbase + buf * kAttTileBytes + mat * (128 * 128) + att_off(r, c);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
-  stage(h0, 0);
-  for (int hi = 0; hi < kAttHeadsPerCta; ++hi) {
-    const int h = h0 + hi, buf = hi & 1;
-    if (hi + 1 < kAttHeadsPerCta) {
-      stage(h + 1, buf ^ 1);                                  // next head streams in while this one is computed
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    const uint32_t sQ = sbase + buf * kAttTileBytes, sK = sQ + 128 * 128, sV = sQ + 2 * 128 * 128;
-
-    // ---- S = Q K^T : 16 x 128 per warp ----
-    uint32_t qf[4][4];
-#pragma unroll
-    for (int kt = 0; kt < 4; ++kt) {
-      const int r = m0 + (lane & 15);          // lanes 0-15: rows 0-15 (k chunk 2kt); lanes 16-31: same rows, chunk 2kt+1
-      const int c = 2 * kt + (lane >> 4);
-      ldsm_x4(qf[kt], sQ + att_off(r, c));
-    }
-    float s[16][4];
-#pragma unroll
-    for (int nt = 0; nt < 16; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f; }
-#pragma unroll
-    for (int np = 0; np < 8; ++np) {            // pairs of 8-key tiles
-#pragma unroll
-      for (int kt = 0; kt < 4; ++kt) {
-        // matrices: (keys np*16+0..7, k chunk 2kt), (same keys, chunk 2kt+1), (keys +8.., chunk 2kt), (keys +8.., chunk 2kt+1)
-        const int r = np * 16 + (lane & 7) + ((lane >> 4) << 3);
-        const int c = 2 * kt + ((lane >> 3) & 1);
-        uint32_t kf[4];
-        ldsm_x4(kf, sK + att_off(r, c));
-        mma16816<BF16>(s[2 * np], qf[kt], kf[0], kf[1]);
-        mma16816<BF16>(s[2 * np + 1], qf[kt], kf[2], kf[3]);
-      }
-    }
-
-    // ---- softmax over the n_valid keys (rows g and g+8 of this warp's 16) ----
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-    for (int nt = 0; nt < 16; ++nt) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int key = nt * 8 + 2 * t + j;
-        if (key >= n_valid) { s[nt][j] = -INFINITY; s[nt][2 + j] = -INFINITY; }
-        mx0 = fmaxf(mx0, s[nt][j]);
-        mx1 = fmaxf(mx1, s[nt][2 + j]);
-      }
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    // exp(x - m) = 2^((x - m) * log2 e): one FFMA + MUFU.EX2; the probabilities are rounded to 16 bits right after, so the
-    // 2-ulp approximation is far below the operand rounding
-    constexpr float kLog2e = 1.4426950408889634f;
-    const float mb0 = mx0 * kLog2e, mb1 = mx1 * kLog2e;
-    float sum0 = 0.0f, sum1 = 0.0f;
-#pragma unroll
-    for (int nt = 0; nt < 16; ++nt) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        s[nt][j] = exp2f(fmaf(s[nt][j], kLog2e, -mb0)); sum0 += s[nt][j];
-        s[nt][2 + j] = exp2f(fmaf(s[nt][2 + j], kLog2e, -mb1)); sum1 += s[nt][2 + j];
-      }
-    }
-    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
-
-    // ---- O = P V : 16 x 64 per warp ----
-    float o[8][4];
-#pragma unroll
-    for (int nd = 0; nd < 8; ++nd) { o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.0f; }
-#pragma unroll
-    for (int kt = 0; kt < 8; ++kt) {            // 16 keys per step
-      uint32_t pf[4];
-      pf[0] = O::pack(s[2 * kt][0] * inv0, s[2 * kt][1] * inv0);
-      pf[1] = O::pack(s[2 * kt][2] * inv1, s[2 * kt][3] * inv1);
-      pf[2] = O::pack(s[2 * kt + 1][0] * inv0, s[2 * kt + 1][1] * inv0);
-      pf[3] = O::pack(s[2 * kt + 1][2] * inv1, s[2 * kt + 1][3] * inv1);
-#pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {          // pairs of 8-wide d tiles
-        // trans matrices: (keys kt*16+0..7, d chunk 2dp), (keys +8.., chunk 2dp), (keys 0..7, chunk 2dp+1), (keys +8.., chunk 2dp+1)
-        const int r = kt * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
-        const int c = 2 * dp + (lane >> 4);
-        uint32_t vf[4];
-        ldsm_x4_trans(vf, sV + att_off(r, c));
-        mma16816<BF16>(o[2 * dp], pf, vf[0], vf[1]);
-        mma16816<BF16>(o[2 * dp + 1], pf, vf[2], vf[3]);
-      }
-    }
-
-    // ---- store (heads compact: col = h*head_dim + d, d < head_dim) ----
-    T* out0 = att + (row0 + m0 + g) * ldo + h * head_dim;
-    T* out1 = out0 + 8 * static_cast<size_t>(ldo);
-#pragma unroll
-    for (int nd = 0; nd < 8; ++nd) {
-      const int d = nd * 8 + 2 * t;
-      if (d < head_dim) {                        // head_dim is even: a pair never straddles the boundary
-        *reinterpret_cast<uint32_t*>(out0 + d) = O::pack(o[nd][0], o[nd][1]);
-        *reinterpret_cast<uint32_t*>(out1 + d) = O::pack(o[nd][2], o[nd][3]);
-      }
-    }
-    __syncthreads();                             // everyone is done with `buf` before the head after next overwrites it
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_att);
+    mbar_init(qk_full, 1); mbar_init(v_full, 1); mbar_init(s_full, 1); mbar_init(o_full, 1);
+    mbar_init(p_ready, 128); mbar_init(o_done, 128);
+    fence_mbar_init();
   }
+  if (warp == 0) tmem_alloc(tmem_ptr, kAttTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_f16(128, 128, BF16 ? 1 : 0);                 // A, B K-major
+      constexpr uint32_t idesc_o = make_idesc_f16(128, 64, BF16 ? 1 : 0) | (1u << 16);     // B (= V) MN-major
+      const uint32_t sQ = smem_u32(smem + kAttOffQ), sK = smem_u32(smem + kAttOffK), sV = smem_u32(smem + kAttOffV), sP = smem_u32(smem + kAttOffP);
+      auto load_qk = [&](int h) {
+        mbar_arrive_expect_tx(qk_full, 2 * kAttTile);
+        tma_load_2d(smem + kAttOffQ, &map_qkv, qk_full, h * 64, row0);
+        tma_load_2d(smem + kAttOffK, &map_qkv, qk_full, n_heads * 64 + h * 64, row0);
+      };
+      auto load_v = [&](int h) {
+        mbar_arrive_expect_tx(v_full, kAttTile);
+        tma_load_2d(smem + kAttOffV, &map_qkv, v_full, 2 * n_heads * 64 + h * 64, row0);
+      };
+      load_qk(h0);
+      load_v(h0);
+      for (int hi = 0; hi < kAttHeadsPerCta; ++hi) {
+        const uint32_t ph = hi & 1;
+        // ---- S = Q K^T ----
+        mbar_wait(qk_full, ph);
+        tc_fence_after();
+        {
+          const uint64_t da = make_smem_desc_sw128(sQ), db = make_smem_desc_sw128(sK);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tS, da + 2 * k, db + 2 * k, idesc_s, k != 0);
+        }
+        umma_commit(s_full);
+        mbar_wait(s_full, ph);                                   // Q, K tiles are free again
+        if (hi + 1 < kAttHeadsPerCta) load_qk(h0 + hi + 1);
+        // ---- O = P V ----
+        mbar_wait(p_ready, ph);                                  // P written (and S fully read)
+        mbar_wait(v_full, ph);
+        if (hi > 0) mbar_wait(o_done, (hi - 1) & 1);             // previous O has been read out of TMEM
+        tc_fence_after();
+        {
+          const uint64_t da = make_smem_desc_sw128(sP), db = make_smem_desc_mn_sw128(sV);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)                            // 16 keys per MMA: P advances 32 B inside a k-block / 16 KB
+            umma_f16(tO, da + (k >> 2) * (kAttTile >> 4) + 2 * (k & 3), db + k * (2048 >> 4), idesc_o, k != 0);   // V: 16 rows
+        }
+        umma_commit(o_full);
+        mbar_wait(o_full, ph);                                   // V (and P) are free again
+        if (hi + 1 < kAttHeadsPerCta) load_v(h0 + hi + 1);
+      }
+    }
+  } else {
+    // ===================== softmax / output warps: thread = query row =====================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;                              // row of the 128-row tile
+    const uint32_t tl = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t sP = smem_u32(smem + kAttOffP), sO = smem_u32(smem + kAttOffO);
+    constexpr float kLog2e = 1.4426950408889634f;
+    for (int hi = 0; hi < kAttHeadsPerCta; ++hi) {
+      const uint32_t ph = hi & 1;
+      const int h = h0 + hi;
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      // pass 1: row maximum over the valid keys
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld<32>(tS + tl + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (c * 32 + j < n_valid) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
+      // pass 2: e = 2^((s - max) log2 e) kept in registers, row sum
+      const float mb = mx * kLog2e;
+      float e[128];
+      float sum = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld<32>(tS + tl + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = (c * 32 + j < n_valid) ? exp2f(fmaf(__uint_as_float(v[j]), kLog2e, -mb)) : 0.0f;
+          e[c * 32 + j] = x;
+          sum += x;
+        }
+      }
+      const float inv = 1.0f / sum;
+      // normalised probabilities, rounded to the operand dtype, as the K-major P tile (2 k-blocks of 64 keys, 128B swizzle)
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const uint4 pk = make_uint4(O::pack(e[8 * c] * inv, e[8 * c + 1] * inv), O::pack(e[8 * c + 2] * inv, e[8 * c + 3] * inv),
+                                    O::pack(e[8 * c + 4] * inv, e[8 * c + 5] * inv), O::pack(e[8 * c + 6] * inv, e[8 * c + 7] * inv));
+        sts_u4(sP + (c >> 3) * kAttTile + r * 128 + (((c & 7) ^ (r & 7)) << 4), pk);
+      }
+      fence_proxy_async();                                       // generic-proxy writes -> visible to the tensor core
+      tc_fence_before();
+      mbar_arrive(p_ready);
+      // ---- output ----
+      mbar_wait(o_full, ph);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld<32>(tO + tl, o0);
+      tmem_ld<32>(tO + tl + 32, o1);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(o_done);                                       // TMEM O may be overwritten by the next head
+      if (warp == 1 && lane == 0) bulk_wait_read0();             // the previous head's TMA store has read the staging tile
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t* s = c < 4 ? o0 + 8 * c : o1 + 8 * (c - 4);
+        const uint4 pk = make_uint4(O::pack(__uint_as_float(s[0]), __uint_as_float(s[1])), O::pack(__uint_as_float(s[2]), __uint_as_float(s[3])),
+                                    O::pack(__uint_as_float(s[4]), __uint_as_float(s[5])), O::pack(__uint_as_float(s[6]), __uint_as_float(s[7])));
+        sts_u4(sO + r * 128 + ((c ^ (r & 7)) << 4), pk);
+      }
+      fence_proxy_async();
+      named_bar_sync(1, 128);
+      if (warp == 1 && lane == 0) { tma_store_2d(&map_att, sO, h * 64, row0); bulk_commit(); }
+    }
+    if (warp == 1 && lane == 0) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, kAttTmemCols); }
 }
 
 }  // namespace ldm

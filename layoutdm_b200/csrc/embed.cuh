@@ -26,17 +26,18 @@ __global__ void adaln_table_kernel(const float* __restrict__ emb /*[L][T][d]*/, 
 }
 
 // fp32 -> 16-bit operand conversion with optional row/col repacking: dst[r][c] = src[src_row(r)][c] for c < src_cols,
-// zero elsewhere.  row_map == nullptr: identity.
+// zero elsewhere.  row_map / col_map == nullptr: identity (maps give the source row / column, -1 = zero).
 template <bool BF16>
 __global__ void pack_weight_kernel(const float* __restrict__ src, void* __restrict__ dst_, const int* __restrict__ row_map,
-                                   int dst_rows, int dst_cols, int src_cols) {
+                                   const int* __restrict__ col_map, int dst_rows, int dst_cols, int src_cols) {
   using O = OpT<BF16>;
   typename O::T* dst = static_cast<typename O::T*>(dst_);
   const size_t n = static_cast<size_t>(dst_rows) * dst_cols;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(i / dst_cols), c = static_cast<int>(i % dst_cols);
     const int sr = row_map ? row_map[r] : r;
-    const float v = (sr >= 0 && c < src_cols) ? src[static_cast<size_t>(sr) * src_cols + c] : 0.0f;
+    const int sc = col_map ? col_map[c] : (c < src_cols ? c : -1);
+    const float v = (sr >= 0 && sc >= 0) ? src[static_cast<size_t>(sr) * src_cols + sc] : 0.0f;
     dst[i] = O::from(v);
   }
 }

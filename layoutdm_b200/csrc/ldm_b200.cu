@@ -37,6 +37,7 @@ int fail(int code, const char* fmt, ...) {
 constexpr int kMaxLayers = 16;
 constexpr int kHeadPad = 64;        // per-head width after padding 58 -> 64
 constexpr int kQkvN = 3 * 8 * kHeadPad;   // 1536
+constexpr int kAttN = 8 * kHeadPad;        // 512: attention output, heads padded like Q/K/V
 constexpr int kLogitLd = 160;       // padded logits row (C <= 160)
 constexpr int kFF1Tile = 232;       // FF1 N tile (1856 = 8 * 232), computed as UMMA_N = 240
 
@@ -131,7 +132,7 @@ struct LdmHandle {
   long long* ids[2] = {nullptr, nullptr};
   long long* ids_final = nullptr;
   long long *c_seq = nullptr, *c_seq_orig = nullptr; unsigned char* c_mask = nullptr; float* c_tbl = nullptr;  // staging for ldm_sample_host
-  CUtensorMap m_x16, m_att16, m_z16, m_hid16;                       // A operands (128 x 64 boxes)
+  CUtensorMap m_x16, m_att16, m_z16, m_hid16, m_qkv16;                       // A operands (128 x 64 boxes)
   CUtensorMap b_qkv16, b_hid16, b_z16, b_x16, b_x32, b_y32, b_logits;  // epilogue 32 x 32 blocks
   std::vector<void*> owned;
 };
@@ -152,12 +153,13 @@ int dev_upload(LdmHandle* h, T** p, const T* src, size_t n) {
   return LDM_OK;
 }
 
-int pack16(LdmHandle* h, void** dst, const float* src_dev, const int* row_map_dev, int dst_rows, int dst_cols, int src_cols) {
+int pack16(LdmHandle* h, void** dst, const float* src_dev, const int* row_map_dev, int dst_rows, int dst_cols, int src_cols,
+           const int* col_map_dev = nullptr) {
   CK(cudaMalloc(dst, static_cast<size_t>(dst_rows) * dst_cols * 2));
   h->owned.push_back(*dst);
   const int blocks = 512;
-  if (h->bf16) pack_weight_kernel<true><<<blocks, 256>>>(src_dev, *dst, row_map_dev, dst_rows, dst_cols, src_cols);
-  else pack_weight_kernel<false><<<blocks, 256>>>(src_dev, *dst, row_map_dev, dst_rows, dst_cols, src_cols);
+  if (h->bf16) pack_weight_kernel<true><<<blocks, 256>>>(src_dev, *dst, row_map_dev, col_map_dev, dst_rows, dst_cols, src_cols);
+  else pack_weight_kernel<false><<<blocks, 256>>>(src_dev, *dst, row_map_dev, col_map_dev, dst_rows, dst_cols, src_cols);
   CK(cudaGetLastError());
   return LDM_OK;
 }
@@ -223,7 +225,7 @@ int ensure_workspace(LdmHandle* h, int n_layouts) {
   const int d = h->desc.d_model, ff = h->desc.d_ff;
   CK(cudaMalloc(&h->x16, M * d * 2));
   CK(cudaMalloc(&h->qkv16, M * kQkvN * 2));
-  CK(cudaMalloc(&h->att16, M * d * 2));
+  CK(cudaMalloc(&h->att16, M * kAttN * 2));
   CK(cudaMalloc(&h->z16, M * d * 2));
   CK(cudaMalloc(&h->hid16, M * ff * 2));
   CK(cudaMalloc(reinterpret_cast<void**>(&h->x32), M * d * 4));
@@ -238,14 +240,15 @@ int ensure_workspace(LdmHandle* h, int n_layouts) {
   CK(cudaMalloc(reinterpret_cast<void**>(&h->c_seq_orig), nid * 8));
   CK(cudaMalloc(reinterpret_cast<void**>(&h->c_mask), nid));
   // zero once: the padding layout (odd batch sizes) and the 3 padding rows of every layout tile must stay finite
-  CK(cudaMemset(h->x16, 0, M * d * 2)); CK(cudaMemset(h->qkv16, 0, M * kQkvN * 2)); CK(cudaMemset(h->att16, 0, M * d * 2));
+  CK(cudaMemset(h->x16, 0, M * d * 2)); CK(cudaMemset(h->qkv16, 0, M * kQkvN * 2)); CK(cudaMemset(h->att16, 0, M * kAttN * 2));
   CK(cudaMemset(h->z16, 0, M * d * 2)); CK(cudaMemset(h->hid16, 0, M * ff * 2)); CK(cudaMemset(h->x32, 0, M * d * 4));
   CK(cudaMemset(h->y32, 0, M * d * 4)); CK(cudaMemset(h->g32, 0, M * d * 4));
   CK(cudaMemset(h->logits, 0, M * kLogitLd * 4));
   h->cap = n_layouts;
   int rc;
   if ((rc = make_map(&h->m_x16, h->x16, M, d, kBM, h->bf16))) return rc;
-  if ((rc = make_map(&h->m_att16, h->att16, M, d, kBM, h->bf16))) return rc;
+  if ((rc = make_map(&h->m_att16, h->att16, M, kAttN, kBM, h->bf16))) return rc;   // attention's TMA store target and the out-projection's A operand
+  if ((rc = make_map(&h->m_qkv16, h->qkv16, M, kQkvN, kBM, h->bf16))) return rc;  // attention's Q / K / V head tiles
   if ((rc = make_map(&h->m_z16, h->z16, M, d, kBM, h->bf16))) return rc;
   if ((rc = make_map(&h->m_hid16, h->hid16, M, ff, kBM, h->bf16))) return rc;
   if ((rc = make_block_map(&h->b_qkv16, h->qkv16, M, kQkvN, 2, h->bf16))) return rc;
@@ -286,11 +289,11 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     LDM_STAGE_DONE();
     {
       ProfScope ps(h, CAT_ATTN, st);
-      attention_kernel<BF16><<<np * (h->desc.n_heads / kAttHeadsPerCta), kAttThreads, kAttSmemBytes, st>>>(h->qkv16, h->att16, h->S, d / h->desc.n_heads, h->desc.n_heads);
+      attention_kernel<BF16><<<np * (h->desc.n_heads / kAttHeadsPerCta), kAttThreads, kAttSmemBytes, st>>>(h->m_qkv16, h->m_att16, h->S, h->desc.n_heads);
     }
     LDM_STAGE_DONE();
     {  // out-projection + bias + residual (from the NORMALISED x) -> y32 ; z16 = LayerNorm2(y)   [fused epilogue]
-      GemmParams p{M, d, d, d / kFF1Tile, h->bo[l], h->z16, d, 1.0f, 0, h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr};
+      GemmParams p{M, d, kAttN, d / kFF1Tile, h->bo[l], h->z16, d, 1.0f, 0, h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr};
       p.dbg = h->gemm_dbg;
       ProfScope ps(h, CAT_OUTPROJ, st);
       gemm_tc_kernel<kFF1Tile, 240, 4, EPI_LN, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<240, 4, EPI_LN>::kBytes, st>>>(
@@ -448,6 +451,10 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   }
   int* qmap_dev = nullptr;
   TRY(dev_upload(h, &qmap_dev, qmap.data(), qmap.size()));
+  std::vector<int> amap(kAttN);
+  for (int c = 0; c < kAttN; ++c) amap[c] = (c % kHeadPad) < dh ? (c / kHeadPad) * dh + (c % kHeadPad) : -1;
+  int* amap_dev = nullptr;
+  TRY(dev_upload(h, &amap_dev, amap.data(), amap.size()));
 
   for (int l = 0; l < L; ++l) {
     float* tmp = nullptr;
@@ -457,7 +464,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
     for (int r = 0; r < kQkvN; ++r) if (qmap[r] >= 0) bq[r] = w->in_proj_b[static_cast<size_t>(l) * 3 * d + qmap[r]];
     TRY(dev_upload(h, &h->bqkv[l], bq.data(), bq.size()));
     TRY(dev_upload(h, &tmp, w->out_proj_w + static_cast<size_t>(l) * d * d, static_cast<size_t>(d) * d));
-    TRY(pack16(h, &h->wo[l], tmp, nullptr, d, d, d));
+    TRY(pack16(h, &h->wo[l], tmp, nullptr, d, kAttN, d, amap_dev));      // K = 512: head h occupies columns h*64 .. h*64+57
     TRY(dev_upload(h, &h->bo[l], w->out_proj_b + static_cast<size_t>(l) * d, static_cast<size_t>(d)));
     TRY(dev_upload(h, &tmp, w->linear1_w + static_cast<size_t>(l) * ff * d, static_cast<size_t>(ff) * d));
     TRY(pack16(h, &h->w1[l], tmp, nullptr, ff, d, d));
@@ -468,7 +475,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
     TRY(dev_upload(h, &h->ln2w[l], w->norm2_w + static_cast<size_t>(l) * d, static_cast<size_t>(d)));
     TRY(dev_upload(h, &h->ln2b[l], w->norm2_b + static_cast<size_t>(l) * d, static_cast<size_t>(d)));
     TRY(make_map(&h->m_wqkv[l], h->wqkv[l], kQkvN, d, 128, h->bf16));   // each CTA of a pair loads half of the weight tile
-    TRY(make_map(&h->m_wo[l], h->wo[l], d, d, 120, h->bf16));
+    TRY(make_map(&h->m_wo[l], h->wo[l], d, kAttN, 120, h->bf16));
     TRY(make_map(&h->m_w1[l], h->w1[l], ff, d, 120, h->bf16));
     TRY(make_map(&h->m_w2[l], h->w2[l], d, ff, 120, h->bf16));
   }
@@ -649,7 +656,7 @@ int64_t ldm_debug_read(const LdmHandle* h, const char* name, void* dst, int64_t 
   else if (!strcmp(name, "g32")) { src = h->g32; bytes = M * d * 4; }
   else if (!strcmp(name, "x16")) { src = h->x16; bytes = M * d * 2; }
   else if (!strcmp(name, "z16")) { src = h->z16; bytes = M * d * 2; }
-  else if (!strcmp(name, "att16")) { src = h->att16; bytes = M * d * 2; }
+  else if (!strcmp(name, "att16")) { src = h->att16; bytes = M * kAttN * 2; }
   else if (!strcmp(name, "qkv16")) { src = h->qkv16; bytes = M * kQkvN * 2; }
   else if (!strcmp(name, "hid16")) { src = h->hid16; bytes = M * ff * 2; }
   else if (!strcmp(name, "logits")) { src = h->logits; bytes = M * kLogitLd * 4; }

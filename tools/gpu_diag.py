@@ -93,7 +93,9 @@ def main():
             cmp(f"L{l}.qkv.q", q, taps[f"q{l}"]); cmp(f"L{l}.qkv.k", k, taps[f"k{l}"]); cmp(f"L{l}.qkv.v", v, taps[f"v{l}"])
             rec(stage=f"L{l}.qkv.pad_cols", max_abs=pad)
             stage += 1; run(stage)
-            cmp(f"L{l}.attention", G.debug_read(eng, "att16", B)[:, :S], taps[f"att{l}"])
+            a16 = G.debug_read(eng, "att16", B)[:, :S].view(B, S, 8, 64)
+            cmp(f"L{l}.attention", a16[..., :58].reshape(B, S, 464), taps[f"att{l}"])
+            rec(stage=f"L{l}.attention.pad_cols", max_abs=float(a16[..., 58:].abs().max()))
             stage += 1; run(stage)      # out-proj GEMM with fused residual + LayerNorm2
             cmp(f"L{l}.outproj.y32", G.debug_read(eng, "y32", B)[:, :S], taps[f"y{l}"])
             cmp(f"L{l}.outproj.z16", G.debug_read(eng, "z16", B)[:, :S], taps[f"z{l}"])
