@@ -6,7 +6,7 @@
 // Output att [M][512] 16-bit, head h in cols [h*64, h*64+64) (cols 58..63 of every head are exact zeros; the out-projection
 //        weight is packed with matching zero columns) = A operand of the out-projection.
 //
-// One CTA = 4 heads of one layout (128 query rows x 128 keys per head), 160 threads, two CTAs per SM:
+// Persistent CTAs (two per SM, 160 threads) walk the (layout, head) work items, 128 query rows x 128 keys each:
 //   warp 0 (one thread) : TMA loads of the Q / K / V head tiles (128B swizzle) and all tcgen05.mma issue:
 //                           S[128x128] = Q K^T      A = Q (K-major), B = K (K-major), 4 MMAs of k=16, fp32 in TMEM cols 0..127
 //                           O[128x64]  = P V        A = P (K-major, written by the softmax warps), B = V as loaded
@@ -22,7 +22,6 @@
 namespace ldm {
 
 constexpr int kAttThreads = 160;
-constexpr int kAttHeadsPerCta = 4;
 constexpr int kAttTile = 128 * 128;                 // one 128 x 64 16-bit tile = 16 KB
 // smem: Q | K | V | P (2 k-blocks) | O staging | barriers
 constexpr int kAttOffQ = 0, kAttOffK = kAttTile, kAttOffV = 2 * kAttTile, kAttOffP = 3 * kAttTile, kAttOffO = 5 * kAttTile;
@@ -44,7 +43,8 @@ LDM_DEVINL uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr) {
 template <bool BF16>
 __global__ void __launch_bounds__(kAttThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64 x 128*/,
-                 const __grid_constant__ CUtensorMap map_att /*[M][512], box 64 x 128*/, int n_valid /*125*/, int n_heads /*8*/) {
+                 const __grid_constant__ CUtensorMap map_att /*[M][512], box 64 x 128*/, int n_valid /*125*/, int n_heads /*8*/,
+                 int n_layouts) {
   using O = OpT<BF16>;
   extern __shared__ uint8_t att_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -58,9 +58,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int groups = n_heads / kAttHeadsPerCta;
-  const int layout = blockIdx.x / groups, h0 = (blockIdx.x % groups) * kAttHeadsPerCta;
-  const int row0 = layout * 128;
+  const int n_items = n_layouts * n_heads;                     // item = layout * n_heads + head
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_qkv);
@@ -81,19 +79,23 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
       constexpr uint32_t idesc_s = make_idesc_f16(128, 128, BF16 ? 1 : 0);                 // A, B K-major
       constexpr uint32_t idesc_o = make_idesc_f16(128, 64, BF16 ? 1 : 0) | (1u << 16);     // B (= V) MN-major
       const uint32_t sQ = smem_u32(smem + kAttOffQ), sK = smem_u32(smem + kAttOffK), sV = smem_u32(smem + kAttOffV), sP = smem_u32(smem + kAttOffP);
-      auto load_qk = [&](int h) {
+      auto load_qk = [&](int item) {
+        const int h = item % n_heads, row0 = (item / n_heads) * 128;
         mbar_arrive_expect_tx(qk_full, 2 * kAttTile);
         tma_load_2d(smem + kAttOffQ, &map_qkv, qk_full, h * 64, row0);
         tma_load_2d(smem + kAttOffK, &map_qkv, qk_full, n_heads * 64 + h * 64, row0);
       };
-      auto load_v = [&](int h) {
+      auto load_v = [&](int item) {
+        const int h = item % n_heads, row0 = (item / n_heads) * 128;
         mbar_arrive_expect_tx(v_full, kAttTile);
         tma_load_2d(smem + kAttOffV, &map_qkv, v_full, 2 * n_heads * 64 + h * 64, row0);
       };
-      load_qk(h0);
-      load_v(h0);
-      for (int hi = 0; hi < kAttHeadsPerCta; ++hi) {
+      const int step = gridDim.x;
+      if (static_cast<int>(blockIdx.x) < n_items) { load_qk(blockIdx.x); load_v(blockIdx.x); }
+      int hi = 0;
+      for (int item = blockIdx.x; item < n_items; item += step, ++hi) {
         const uint32_t ph = hi & 1;
+        const bool has_next = item + step < n_items;
         // ---- S = Q K^T ----
         mbar_wait(qk_full, ph);
         tc_fence_after();
@@ -104,7 +106,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
         }
         umma_commit(s_full);
         mbar_wait(s_full, ph);                                   // Q, K tiles are free again
-        if (hi + 1 < kAttHeadsPerCta) load_qk(h0 + hi + 1);
+        if (has_next) load_qk(item + step);
         // ---- O = P V ----
         mbar_wait(p_ready, ph);                                  // P written (and S fully read)
         mbar_wait(v_full, ph);
@@ -118,7 +120,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
         }
         umma_commit(o_full);
         mbar_wait(o_full, ph);                                   // V (and P) are free again
-        if (hi + 1 < kAttHeadsPerCta) load_v(h0 + hi + 1);
+        if (has_next) load_v(item + step);
       }
     }
   } else {
@@ -128,9 +130,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
     const uint32_t tl = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t sP = smem_u32(smem + kAttOffP), sO = smem_u32(smem + kAttOffO);
     constexpr float kLog2e = 1.4426950408889634f;
-    for (int hi = 0; hi < kAttHeadsPerCta; ++hi) {
+    int hi = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++hi) {
       const uint32_t ph = hi & 1;
-      const int h = h0 + hi;
+      const int h = item % n_heads, row0 = (item / n_heads) * 128;
       mbar_wait(s_full, ph);
       tc_fence_after();
       // pass 1: row maximum over the valid keys
