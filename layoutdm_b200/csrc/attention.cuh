@@ -14,8 +14,8 @@
 //   warps 1..4          : thread = query row.  Exact softmax from TMEM (max pass, then exp2 / sum in registers), the
 //                         normalised probabilities are rounded to the operand dtype and written as the P operand tile;
 //                         later O is read back from TMEM, packed and TMA-stored.
-// The next head's Q/K tiles are requested as soon as the S MMAs have retired, the next V once the PV MMAs have retired, so
-// the loads overlap the softmax; the second CTA on the SM fills the remaining bubbles.
+// The next item's tiles are requested once the PV MMAs have retired (P lives in the Q | K area); the other two CTAs on the SM
+// fill the bubbles.
 #pragma once
 #include "common.cuh"
 
@@ -23,11 +23,12 @@ namespace ldm {
 
 constexpr int kAttThreads = 160;
 constexpr int kAttTile = 128 * 128;                 // one 128 x 64 16-bit tile = 16 KB
-// smem: Q | K | V | P (2 k-blocks) | O staging | barriers
-constexpr int kAttOffQ = 0, kAttOffK = kAttTile, kAttOffV = 2 * kAttTile, kAttOffP = 3 * kAttTile, kAttOffO = 5 * kAttTile;
-constexpr int kAttOffBar = 6 * kAttTile;
-constexpr int kAttSmemBytes = 6 * kAttTile + 128 + 1024;   // + barriers + alignment slack
-constexpr uint32_t kAttTmemCols = 256;              // S: cols 0..127, O: cols 128..191
+// smem: Q | K (later overwritten by the 2 k-blocks of P: Q and K are dead once the S MMAs retired) | V | O staging | barriers
+// 64 KB + TMEM 128 columns per CTA -> three CTAs per SM
+constexpr int kAttOffQ = 0, kAttOffK = kAttTile, kAttOffP = 0, kAttOffV = 2 * kAttTile, kAttOffO = 3 * kAttTile;
+constexpr int kAttOffBar = 4 * kAttTile;
+constexpr int kAttSmemBytes = 4 * kAttTile + 128 + 1024;   // + barriers + alignment slack
+constexpr uint32_t kAttTmemCols = 128;              // S: cols 0..127; O reuses cols 0..63 once the softmax has consumed S
 
 // MN-major (rows = K index, 64 contiguous 16-bit elements = N) operand tile with 128-byte swizzle, 8-row groups 1024 B apart
 LDM_DEVINL uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr) {
@@ -41,7 +42,7 @@ LDM_DEVINL uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr) {
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(kAttThreads, 2)
+__global__ void __launch_bounds__(kAttThreads, 3)
 attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64 x 128*/,
                  const __grid_constant__ CUtensorMap map_att /*[M][512], box 64 x 128*/, int n_valid /*125*/, int n_heads /*8*/,
                  int n_layouts) {
@@ -72,7 +73,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t tS = tmem_base, tO = tmem_base;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -105,8 +106,6 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
           for (int k = 0; k < 4; ++k) umma_f16(tS, da + 2 * k, db + 2 * k, idesc_s, k != 0);
         }
         umma_commit(s_full);
-        mbar_wait(s_full, ph);                                   // Q, K tiles are free again
-        if (has_next) load_qk(item + step);
         // ---- O = P V ----
         mbar_wait(p_ready, ph);                                  // P written (and S fully read)
         mbar_wait(v_full, ph);
@@ -119,8 +118,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
             umma_f16(tO, da + (k >> 2) * (kAttTile >> 4) + 2 * (k & 3), db + k * (2048 >> 4), idesc_o, k != 0);   // V: 16 rows
         }
         umma_commit(o_full);
-        mbar_wait(o_full, ph);                                   // V (and P) are free again
-        if (has_next) load_v(item + step);
+        mbar_wait(o_full, ph);                                   // P (= the Q | K area) and V are free again
+        if (has_next) { load_qk(item + step); load_v(item + step); }
       }
     }
   } else {

@@ -289,7 +289,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     LDM_STAGE_DONE();
     {
       ProfScope ps(h, CAT_ATTN, st);
-      attention_kernel<BF16><<<std::min(np * h->desc.n_heads, 2 * h->num_sms), kAttThreads, kAttSmemBytes, st>>>(h->m_qkv16, h->m_att16, h->S, h->desc.n_heads, np);
+      attention_kernel<BF16><<<std::min(np * h->desc.n_heads, 3 * h->num_sms), kAttThreads, kAttSmemBytes, st>>>(h->m_qkv16, h->m_att16, h->S, h->desc.n_heads, np);
     }
     LDM_STAGE_DONE();
     {  // out-projection + bias + residual (from the NORMALISED x) -> y32 ; z16 = LayerNorm2(y)   [fused epilogue]
