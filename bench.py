@@ -37,6 +37,15 @@ FLOPS = {"qkv_gemm": 161_472_000, "outproj_gemm": 53_824_000, "ff1_gemm": 215_29
 FLOPS_PER_LAYOUT_STEP = 2_717_532_000
 
 
+def load_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json)"""
+    try:
+        d = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json")))
+        return float(d["dram_bytes_per_launch"][kernel]), d["source"]
+    except Exception:
+        return None, None
+
+
 def load_peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -243,8 +252,10 @@ def run_b200_arm(args, world, rank, local):
     dom_ms, dom_n = gemm[dom]
     achieved = FLOPS[dom] * B / (dom_ms / dom_n * 1e-3) / 1e12
     tot_prof = sum(v[0] for v in prof.values())
+    traffic, traffic_src = load_traffic(dom) if B == 1024 else (None, None)
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["sustained"], "traffic": None, "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
+                "frac": achieved / peaks["sustained"], "traffic": traffic, "traffic_unit": "bytes/launch", "traffic_source": traffic_src,
+                "algorithmic_flops_per_launch": FLOPS[dom] * B, "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
                 "share_of_step": dom_ms / tot_prof,
                 "kernels": {k: {"ms_per_pass": round(v[0], 3), "launches": v[1], "share": round(v[0] / tot_prof, 4),
                                 **({"tflops": round(FLOPS[k] * B / (v[0] / v[1] * 1e-3) / 1e12, 1)} if k in FLOPS and v[1] else {})}
