@@ -145,14 +145,14 @@ int64_t ldm_get_adaln_table(const LdmHandle* h, float* dst_host, int64_t capacit
 
 /* Per-kernel timing for bench.py's roofline: between begin and end every launch is bracketed by a CUDA-event pair on
  * the launching stream; end() synchronises and returns the summed milliseconds and launch counts per category:
- * 0 embed+AdaLN, 1 QKV GEMM, 2 attention, 3 out-proj GEMM, 4 FF1 GEMM, 5 FF2 GEMM, 6 head GEMM,
- * 7 posterior+sampling epilogue, 8 misc, 9 residual+LayerNorm. */
-#define LDM_PROFILE_CATEGORIES 10
+ * 0 embed+AdaLN, 1 QKV GEMM, 2 attention, 3 out-proj GEMM (+residual+LayerNorm2), 4 FF1 GEMM, 5 FF2 GEMM (+residual+AdaLN /
+ * head LN), 6 head GEMM, 7 posterior+sampling epilogue, 8 misc. */
+#define LDM_PROFILE_CATEGORIES 9
 int ldm_profile_begin(LdmHandle* h);
 int ldm_profile_end(LdmHandle* h, float* ms_per_category, int64_t* launches_per_category, int32_t n_categories);
 
 /* test taps (tests/ and tools/ only): stop the denoiser after n launches (0 = off); read a workspace buffer
- * ("x32","y32","g32","x16","z16","att16","qkv16","hid16","logits") of the first n_layouts layouts to host; returns bytes. */
+ * ("x32","y32","x16","z16","att16","qkv16","hid16","logits") of the first n_layouts layouts to host; returns bytes. */
 int ldm_debug_set_stop_after(LdmHandle* h, int32_t n_launches);
 int64_t ldm_debug_read(const LdmHandle* h, const char* name, void* dst_host, int64_t capacity_bytes, int32_t n_layouts);
 

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libldm_b200.so")
 
 LDM_OK, LDM_ERR_INVALID, LDM_ERR_CUDA, LDM_ERR_UNSUPPORTED = 0, -1, -2, -3
-PROFILE_CATEGORIES = ("embed_adaln", "qkv_gemm", "attention", "outproj_gemm", "ff1_gemm", "ff2_gemm", "head_gemm", "posterior_sample", "misc", "resid_ln")
+PROFILE_CATEGORIES = ("embed_adaln", "qkv_gemm", "attention", "outproj_gemm", "ff1_gemm", "ff2_gemm", "head_gemm", "posterior_sample", "misc")
 SAMPLING_MODES = {"deterministic": 0, "random": 1, "top_k": 2, "top_p": 3, "gumbel": 4}
 
 

@@ -104,69 +104,4 @@ embed_adaln_kernel(const long long* __restrict__ ids /*[B][S]*/, const float* __
   }
 }
 
-// y = g + resid ; out = LN(y) * gamma + beta            (transformer_utils.py:178-179 with norm2 :156 / head LN nn_lib.py:187-189)
-//                  or  LN(y) * (1 + scale_t) + shift_t   (next block's AdaLayerNorm, transformer_utils.py:79-83)
-// g: fp32 GEMM output (bias already added), resid: fp32 residual stream.  One warp per row, two-pass moments in registers.
-template <bool BF16>
-__global__ void __launch_bounds__(256)
-resid_ln_kernel(const float* __restrict__ g, const float* __restrict__ resid, float* __restrict__ y_out /*nullable*/,
-                const float* __restrict__ ln_scale, const float* __restrict__ ln_shift, int adaln,
-                float* __restrict__ out32 /*nullable*/, void* __restrict__ out16_, int n_rows, int d) {
-  using O = OpT<BF16>;
-  typename O::T* out16 = static_cast<typename O::T*>(out16_);
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (row >= n_rows) return;
-  const int nv = d / 4;
-  const size_t base = static_cast<size_t>(row) * d;
-  const float4* g4 = reinterpret_cast<const float4*>(g + base);
-  const float4* r4 = reinterpret_cast<const float4*>(resid + base);
-  float4 v[4];
-  float sum = 0.0f;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int i = lane + 32 * k;
-    if (i < nv) {
-      const float4 a = __ldcs(g4 + i), c = __ldcs(r4 + i);        // streamed once: evict-first
-      v[k] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
-      sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-    } else {
-      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-  if (y_out != nullptr) {
-    float4* y4 = reinterpret_cast<float4*>(y_out + base);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) if (lane + 32 * k < nv) y4[lane + 32 * k] = v[k];
-  }
-  const float mean = warp_sum(sum) / d;
-  float var = 0.0f;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (lane + 32 * k < nv) {
-      const float a = v[k].x - mean, b2 = v[k].y - mean, c = v[k].z - mean, e2 = v[k].w - mean;
-      var += (a * a + b2 * b2) + (c * c + e2 * e2);
-    }
-  }
-  const float rstd = 1.0f / sqrtf(warp_sum(var) / d + 1e-5f);
-  const float gadd = adaln ? 1.0f : 0.0f;
-  const float4* sc = reinterpret_cast<const float4*>(ln_scale);
-  const float4* sh = reinterpret_cast<const float4*>(ln_shift);
-  float4* o32 = out32 != nullptr ? reinterpret_cast<float4*>(out32 + base) : nullptr;
-  uint2* o16 = reinterpret_cast<uint2*>(out16 + base);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int i = lane + 32 * k;
-    if (i < nv) {
-      const float4 gm = __ldg(sc + i), h = __ldg(sh + i);
-      float4 r;
-      r.x = (v[k].x - mean) * rstd * (gm.x + gadd) + h.x;
-      r.y = (v[k].y - mean) * rstd * (gm.y + gadd) + h.y;
-      r.z = (v[k].z - mean) * rstd * (gm.z + gadd) + h.z;
-      r.w = (v[k].w - mean) * rstd * (gm.w + gadd) + h.w;
-      if (o32 != nullptr) o32[i] = r;
-      o16[i] = make_uint2(O::pack(r.x, r.y), O::pack(r.z, r.w));
-    }
-  }
-}
-
 }  // namespace ldm

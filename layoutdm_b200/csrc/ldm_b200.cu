@@ -128,7 +128,7 @@ struct LdmHandle {
   // workspace (device), sized for cap layouts
   int cap = 0;
   void *x16 = nullptr, *qkv16 = nullptr, *att16 = nullptr, *z16 = nullptr, *hid16 = nullptr;
-  float *x32 = nullptr, *y32 = nullptr, *g32 = nullptr, *logits = nullptr;
+  float *x32 = nullptr, *y32 = nullptr, *logits = nullptr;
   long long* ids[2] = {nullptr, nullptr};
   long long* ids_final = nullptr;
   long long *c_seq = nullptr, *c_seq_orig = nullptr; unsigned char* c_mask = nullptr; float* c_tbl = nullptr;  // staging for ldm_sample_host
@@ -194,7 +194,7 @@ void build_schedule(const LdmModelDesc& d, int N, float* out /*[8][T+1]*/) {
   }
 }
 
-enum : int { CAT_EMBED = 0, CAT_QKV, CAT_ATTN, CAT_OUTPROJ, CAT_FF1, CAT_FF2, CAT_HEAD, CAT_EPILOGUE, CAT_MISC, CAT_RESID_LN, CAT_COUNT };
+enum : int { CAT_EMBED = 0, CAT_QKV, CAT_ATTN, CAT_OUTPROJ, CAT_FF1, CAT_FF2, CAT_HEAD, CAT_EPILOGUE, CAT_MISC, CAT_COUNT };
 
 struct ProfScope {   // counts the launch; when profiling is on, brackets it with a CUDA-event pair on the launching stream
   LdmHandle* h; cudaStream_t st; cudaEvent_t b = nullptr;
@@ -219,7 +219,7 @@ int ensure_workspace(LdmHandle* h, int n_layouts) {
   n_layouts = (n_layouts + 1) & ~1;     // GEMM CTA pairs work on 256-row blocks: keep an even number of layout tiles
   if (n_layouts <= h->cap) return LDM_OK;
   // free the old workspace
-  void* olds[] = {h->x16, h->qkv16, h->att16, h->z16, h->hid16, h->x32, h->y32, h->g32, h->logits, h->ids[0], h->ids[1], h->ids_final, h->c_seq, h->c_seq_orig, h->c_mask};
+  void* olds[] = {h->x16, h->qkv16, h->att16, h->z16, h->hid16, h->x32, h->y32, h->logits, h->ids[0], h->ids[1], h->ids_final, h->c_seq, h->c_seq_orig, h->c_mask};
   for (void* p : olds) if (p) cudaFree(p);
   const size_t M = static_cast<size_t>(n_layouts) * kBM;
   const int d = h->desc.d_model, ff = h->desc.d_ff;
@@ -230,7 +230,6 @@ int ensure_workspace(LdmHandle* h, int n_layouts) {
   CK(cudaMalloc(&h->hid16, M * ff * 2));
   CK(cudaMalloc(reinterpret_cast<void**>(&h->x32), M * d * 4));
   CK(cudaMalloc(reinterpret_cast<void**>(&h->y32), M * d * 4));
-  CK(cudaMalloc(reinterpret_cast<void**>(&h->g32), M * d * 4));
   CK(cudaMalloc(reinterpret_cast<void**>(&h->logits), M * kLogitLd * 4));
   const size_t nid = static_cast<size_t>(n_layouts) * h->S;
   CK(cudaMalloc(reinterpret_cast<void**>(&h->ids[0]), nid * 8));
@@ -242,7 +241,7 @@ int ensure_workspace(LdmHandle* h, int n_layouts) {
   // zero once: the padding layout (odd batch sizes) and the 3 padding rows of every layout tile must stay finite
   CK(cudaMemset(h->x16, 0, M * d * 2)); CK(cudaMemset(h->qkv16, 0, M * kQkvN * 2)); CK(cudaMemset(h->att16, 0, M * kAttN * 2));
   CK(cudaMemset(h->z16, 0, M * d * 2)); CK(cudaMemset(h->hid16, 0, M * ff * 2)); CK(cudaMemset(h->x32, 0, M * d * 4));
-  CK(cudaMemset(h->y32, 0, M * d * 4)); CK(cudaMemset(h->g32, 0, M * d * 4));
+  CK(cudaMemset(h->y32, 0, M * d * 4));
   CK(cudaMemset(h->logits, 0, M * kLogitLd * 4));
   h->cap = n_layouts;
   int rc;
@@ -521,7 +520,7 @@ int ldm_destroy(LdmHandle* h) {
   if (!h) return LDM_OK;
   cudaSetDevice(h->desc.device);
   for (void* p : h->owned) cudaFree(p);
-  void* ws[] = {h->x16, h->qkv16, h->att16, h->z16, h->hid16, h->x32, h->y32, h->g32, h->logits, h->ids[0], h->ids[1], h->ids_final, h->c_seq, h->c_seq_orig, h->c_mask, h->c_tbl};
+  void* ws[] = {h->x16, h->qkv16, h->att16, h->z16, h->hid16, h->x32, h->y32, h->logits, h->ids[0], h->ids[1], h->ids_final, h->c_seq, h->c_seq_orig, h->c_mask, h->c_tbl};
   for (void* p : ws) if (p) cudaFree(p);
   delete h;
   return LDM_OK;
@@ -653,7 +652,6 @@ int64_t ldm_debug_read(const LdmHandle* h, const char* name, void* dst, int64_t 
   const void* src = nullptr; size_t bytes = 0;
   if (!strcmp(name, "x32")) { src = h->x32; bytes = M * d * 4; }
   else if (!strcmp(name, "y32")) { src = h->y32; bytes = M * d * 4; }
-  else if (!strcmp(name, "g32")) { src = h->g32; bytes = M * d * 4; }
   else if (!strcmp(name, "x16")) { src = h->x16; bytes = M * d * 2; }
   else if (!strcmp(name, "z16")) { src = h->z16; bytes = M * d * 2; }
   else if (!strcmp(name, "att16")) { src = h->att16; bytes = M * kAttN * 2; }

@@ -11,7 +11,7 @@ def debug_read(engine, name: str, n_layouts: int) -> torch.Tensor:
     lib, h = engine.lib, engine._h
     nbytes = lib.ldm_debug_read(h, name.encode(), None, 0, n_layouts)
     assert nbytes > 0, f"unknown buffer {name}"
-    is32 = name in ("x32", "y32", "g32", "logits")
+    is32 = name in ("x32", "y32", "logits")
     dt = torch.float32 if is32 else (torch.bfloat16 if engine.operand_dtype == "bf16" else torch.float16)
     out = torch.empty(nbytes // (4 if is32 else 2), dtype=dt)
     rc = lib.ldm_debug_read(h, name.encode(), C.c_void_p(out.data_ptr()), nbytes, n_layouts)
