@@ -133,6 +133,18 @@ int ldm_sample_host(LdmHandle* h, int32_t B, int32_t n_steps, const int32_t* t_m
                     int64_t b_global0, const int64_t* ids_init_host, int64_t* ids_out_host, void* stream,
                     int64_t* h2d_bytes, int64_t* d2h_bytes);
 
+/* Forward (corruption) process on ids: x_t ~ q(x_t | x_0) at per-layout timesteps t_dev[B] with the reference's
+ * Gumbel-argmax draw == q_sample / log_sample_categorical (constrained.py:208-230, vanilla.py:153-158) as the training
+ * forward applies it per attribute (constrained.py:232-260).  Noise: Philox stream 2 of the contract in DESIGN.md. */
+int ldm_q_sample(LdmHandle* h, int32_t B, const int64_t* x0_ids_dev, const int32_t* t_dev, uint64_t seed, int64_t b_global0,
+                 int64_t* xt_ids_dev, void* stream);
+
+/* ids -> layouts on the device == LayoutSequenceTokenizer.decode (layout_tokenizer.py:255-266) + BboxTokenizer.decode
+ * (bbox_tokenizer.py:117-174).  centers_dev: [4][n_bins] cluster centres (kmeans / percentile) or NULL for linear bins.
+ * Outputs (device): bbox [B][n_elem][4] f32 (xywh), label [B][n_elem] i64, mask [B][n_elem] u8 (1 = valid element). */
+int ldm_decode(LdmHandle* h, int32_t B, const int64_t* ids_dev, const float* centers_dev, float* bbox_out_dev,
+               int64_t* label_out_dev, uint8_t* mask_out_dev, void* stream);
+
 /* Introspection */
 int64_t ldm_launch_count(const LdmHandle* h);            /* kernels launched by this handle so far */
 int32_t ldm_num_classes(const LdmHandle* h);             /* C */

@@ -616,6 +616,43 @@ int ldm_sample_host(LdmHandle* h, int32_t B, int32_t n_steps, const int32_t* t_m
   return LDM_OK;
 }
 
+int ldm_q_sample(LdmHandle* h, int32_t B, const int64_t* x0, const int32_t* t, uint64_t seed, int64_t b_global0, int64_t* xt, void* stream) {
+  if (!h || !x0 || !t || !xt || B <= 0) return fail(LDM_ERR_INVALID, "bad ldm_q_sample arguments");
+  CK(cudaSetDevice(h->desc.device));
+  QSampleParams p{};
+  p.n_layouts = B; p.S = h->S; p.C = h->C; p.n_attr = h->desc.n_attr; p.pad_id = h->C - 2; p.mask_id = h->C - 1;
+  p.constrained = h->desc.q_type == 0;
+  for (int g = 0; g < h->desc.n_attr && g < kMaxAttr; ++g) {
+    p.grp_start[g] = g == 0 ? 0 : h->desc.n_cat + (g - 1) * h->desc.n_bins;
+    p.grp_n[g] = g == 0 ? h->desc.n_cat : h->desc.n_bins;
+  }
+  p.T = h->T; p.sched = h->sched; p.x0 = reinterpret_cast<const long long*>(x0); p.t = t;
+  p.seed = seed; p.b_global0 = b_global0; p.xt = reinterpret_cast<long long*>(xt);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int warps = B * h->S, blocks = (warps * 32 + 255) / 256;
+  {
+    ProfScope ps(h, CAT_MISC, st);
+    q_sample_kernel<<<blocks, 256, 0, st>>>(p);
+  }
+  CK(cudaGetLastError());
+  return LDM_OK;
+}
+
+int ldm_decode(LdmHandle* h, int32_t B, const int64_t* ids, const float* centers, float* bbox, int64_t* label, uint8_t* mask, void* stream) {
+  if (!h || !ids || !bbox || !label || !mask || B <= 0) return fail(LDM_ERR_INVALID, "bad ldm_decode arguments");
+  if (h->desc.n_attr != 5) return fail(LDM_ERR_UNSUPPORTED, "decode needs the c-x-y-w-h token layout");
+  CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = B * h->desc.n_elem;
+  {
+    ProfScope ps(h, CAT_MISC, st);
+    decode_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(ids), centers, bbox, reinterpret_cast<long long*>(label), mask,
+                                                  B, h->desc.n_elem, h->desc.n_attr, h->desc.n_cat, h->desc.n_bins);
+  }
+  CK(cudaGetLastError());
+  return LDM_OK;
+}
+
 int64_t ldm_launch_count(const LdmHandle* h) { return h ? h->launches : 0; }
 
 int ldm_profile_begin(LdmHandle* h) {

@@ -258,4 +258,86 @@ __global__ void __launch_bounds__(256) posterior_sample_kernel(const StepParams 
   if (lane == 0) p.ids_out[token] = best_c;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Forward (corruption) process on ids: x_t ~ q(x_t | x_0) with the reference's Gumbel-argmax draw.
+// q_pred  T/models/categorical_diffusion/constrained.py:112-133 (vanilla.py:90-110), log_sample_categorical :208-221,
+// q_sample :223-230; the training forward applies it per attribute on the partial vocabularies (:232-260) -- here per token
+// on the full ids (classes outside the token's group are impossible).  One warp per token, same class ownership as above.
+struct QSampleParams {
+  int n_layouts, S, C, n_attr, pad_id, mask_id, constrained;
+  int grp_start[kMaxAttr], grp_n[kMaxAttr];
+  int T;
+  const float* sched;                    // [G][8][T+1]
+  const long long* x0;                   // [n_layouts][S]
+  const int* t;                          // [n_layouts]
+  unsigned long long seed; long long b_global0;
+  long long* xt;                         // [n_layouts][S]
+};
+
+__global__ void __launch_bounds__(256) q_sample_kernel(const QSampleParams p) {
+  const int token = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (token >= p.n_layouts * p.S) return;
+  const int b = token / p.S, s = token % p.S;
+  const int C = p.C;
+  const int x0 = static_cast<int>(p.x0[token]);
+  const int t = p.t[b];
+  const int g = p.constrained ? (s % p.n_attr) : 0;
+  const int gst = p.grp_start[g], gn = p.grp_n[g];
+  const int TT = p.T + 1;
+  const float* tab = p.sched + static_cast<size_t>(g) * 8 * TT;
+  const float lcat = tab[3 * TT + t], lcbt = tab[4 * TT + t], lcct = tab[5 * TT + t], l1m = tab[7 * TT + t];
+  const unsigned long long tok = (static_cast<unsigned long long>(p.b_global0) + b) * static_cast<unsigned long long>(p.S) + s;
+  const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
+  const uint32_t tok_lo = static_cast<uint32_t>(tok), tok_hi = static_cast<uint32_t>(tok >> 32);
+  const uint4 ga = philox4x32_10(make_uint4(static_cast<uint32_t>(lane), 2u << 24, tok_lo, tok_hi), key);
+  const uint4 gb = philox4x32_10(make_uint4(32u + (static_cast<uint32_t>(lane) >> 2), 2u << 24, tok_lo, tok_hi), key);
+  const uint32_t gw[5] = {ga.x, ga.y, ga.z, ga.w, (lane & 3) == 0 ? gb.x : (lane & 3) == 1 ? gb.y : (lane & 3) == 2 ? gb.z : gb.w};
+  float best = -INFINITY; int best_c = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int c = j < 4 ? 4 * lane + j : 128 + lane;
+    const bool in_grp = c < C && (p.constrained ? ((c >= gst && c < gst + gn) || c == p.pad_id || c == p.mask_id) : true);
+    if (!in_grp) continue;
+    const float v = (c == x0) ? 0.0f : kLogEps;                          // log(clamp(onehot, 1e-30))
+    const float logit = (c != p.mask_id) ? log_add_exp(v + lcat, lcbt) : log_add_exp(v + l1m, lcct);
+    const float u = u01_from_bits(gw[j]);
+    const float score = logit + (-logf(-logf(u + 1e-30f) + 1e-30f));
+    if (score > best || (score == best && c < best_c)) { best = score; best_c = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+    if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+  }
+  if (lane == 0) p.xt[token] = best_c;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ids -> layouts on the device: LayoutSequenceTokenizer.decode (T/helpers/layout_tokenizer.py:255-266, :106-114) +
+// BboxTokenizer.decode (T/helpers/bbox_tokenizer.py:117-174).  One thread per element; centers == nullptr: linear bins.
+__global__ void decode_kernel(const long long* __restrict__ ids, const float* __restrict__ centers /*[4][n_bins] or null*/,
+                              float* __restrict__ bbox /*[B][E][4]*/, long long* __restrict__ label /*[B][E]*/,
+                              unsigned char* __restrict__ mask /*[B][E]*/, int n_layouts, int n_elem, int n_attr, int n_cat, int n_bins) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_layouts * n_elem) return;
+  const long long* tk = ids + static_cast<size_t>(i) * n_attr;
+  const long long lab = tk[0];
+  bool valid = lab >= 0 && lab < n_cat;
+  float bb[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const long long v = tk[1 + a] - n_cat;                                // shared_bbox_vocab x-y-w-h: 4 * n_bins ids
+    valid = valid && v >= 0 && v < 4LL * n_bins;
+    long long bin = v - static_cast<long long>(a) * n_bins;
+    bin = bin < 0 ? 0 : (bin > n_bins - 1 ? n_bins - 1 : bin);            // clamp (avoid OOV)
+    if (centers != nullptr) bb[a] = fminf(fmaxf(centers[a * n_bins + bin], 0.0f), 1.0f);
+    else bb[a] = static_cast<float>(a < 2 ? bin : bin + 1) * (1.0f / n_bins);
+  }
+  float4* o = reinterpret_cast<float4*>(bbox) + i;
+  *o = valid ? make_float4(bb[0], bb[1], bb[2], bb[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  label[i] = valid ? lab : 0;
+  mask[i] = valid ? 1 : 0;
+}
+
 }  // namespace ldm

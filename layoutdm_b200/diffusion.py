@@ -152,6 +152,10 @@ class FusedMaskAndReplaceDiffusion:
         self._step_ctr += 1
         return index_to_log_onehot(out, self.num_classes)
 
+    def q_sample_ids(self, x0: torch.Tensor, t: torch.Tensor, seed: Optional[int] = None) -> torch.Tensor:
+        """corruption x_t ~ q(x_t | x_0) on ids (constrained.py:223-230 applied per attribute as in :232-260)"""
+        return self.engine.q_sample(x0, t, self._new_seed() if seed is None else seed)
+
     def reset_noise(self, seed: int):
         self._seed, self._step_ctr = seed, 0
 
@@ -187,6 +191,9 @@ class LayoutDMB200:
         ids = self.model.sample(batch_size=batch_size, cond=cond, sampling_cfg=sampling_cfg, **kw)
         if self.tokenizer is not None:
             return self.tokenizer.decode(ids)
+        if kwargs.get("decode_on_device", False) and not kw.get("get_intermediate_results", False):
+            c = None if self._centers is None else torch.stack([torch.as_tensor(x, dtype=torch.float32).view(-1) for x in self._centers])
+            return {k: v.cpu() for k, v in self.model.engine.decode(ids, c).items()}
         return decode_ids(ids, self.vocab, self._centers)
 
     def aggregate_sampling_settings(self, sampling_cfg, args):

@@ -193,6 +193,28 @@ class Engine:
         _lib.check(rc)
         return (out, tr) if trace else out
 
+    def q_sample(self, x0: torch.Tensor, t: torch.Tensor, seed: int = 0, b_global0: int = 0) -> torch.Tensor:
+        """forward (corruption) process: x0 (B,S) ids, t (B,) timesteps -> x_t ids (CUDA)"""
+        B, S = x0.shape
+        assert S == self.vocab.S and int(t.min()) >= 0 and int(t.max()) < self.T
+        x0 = x0.to(self.device, torch.int64).contiguous()
+        t32 = t.to(self.device, torch.int32).contiguous()
+        out = torch.empty_like(x0)
+        _lib.check(self.lib.ldm_q_sample(self._h, B, _ptr(x0), _ptr(t32), C.c_uint64(seed), C.c_int64(b_global0), _ptr(out), self._stream()))
+        return out
+
+    def decode(self, ids: torch.Tensor, centers: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """ids (B,S) on the GPU -> {"bbox" (B,E,4) f32, "label" (B,E) i64, "mask" (B,E) bool} on the GPU"""
+        B = ids.shape[0]
+        ids = ids.to(self.device, torch.int64).contiguous()
+        E = self.vocab.n_elem
+        bbox = torch.empty(B, E, 4, dtype=torch.float32, device=self.device)
+        label = torch.empty(B, E, dtype=torch.int64, device=self.device)
+        mask = torch.empty(B, E, dtype=torch.uint8, device=self.device)
+        c = None if centers is None else centers.to(self.device, torch.float32).contiguous()
+        _lib.check(self.lib.ldm_decode(self._h, B, _ptr(ids), _ptr(c), _ptr(bbox), _ptr(label), _ptr(mask), self._stream()))
+        return {"bbox": bbox, "label": label, "mask": mask.bool()}
+
     def sample_host(self, B: int, plan, sampling, cond: Optional[dict] = None, seed: int = 0, b_global0: int = 0,
                     ids_init: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
         """host-buffer entry (ldm_sample_host): cond / ids_init are CPU tensors (ideally pinned); returns (ids CPU, h2d, d2h)."""

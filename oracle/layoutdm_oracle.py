@@ -558,3 +558,34 @@ def decode_ids(ids: torch.Tensor, vocab: VocabSpec) -> Dict[str, torch.Tensor]:
     label[invalid] = 0
     out[invalid] = 0.0
     return {"bbox": out, "label": label, "mask": ~invalid}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# forward (corruption) process on ids  (constrained.py:208-230, vanilla.py:153-158; used by training forward :232-260)
+# --------------------------------------------------------------------------------------------------------------
+
+
+def q_sample_ids(x0: torch.Tensor, t: torch.Tensor, T: int, vocab: VocabSpec, scheds: List[Dict[str, torch.Tensor]],
+                 u: np.ndarray, q_type: str = "constrained") -> torch.Tensor:
+    """x0 (B,S) ids, t (B,) per-layout timestep, u (B,S,C) uniforms of the noise contract (stream 2) -> x_t (B,S) ids.
+    Per token: log q(x_t = k | x_0) = q_pred(log_onehot(x_0), t) over the token's vocabulary group, then the reference's
+    Gumbel-argmax draw  argmax_k(logits_k - log(-log(u_k + 1e-30) + 1e-30))  (train_sampling="gumbel")."""
+    B, S = x0.shape
+    C = vocab.C
+    log_x0 = index_to_log_onehot(x0, C)                                   # (B,S,C)
+    ug = torch.from_numpy(u)
+    gumbel = -torch.log(-torch.log(ug + 1e-30) + 1e-30)
+    out = torch.empty_like(x0)
+    groups = range(vocab.n_attr) if q_type == "constrained" else [0]
+    for g in groups:
+        idx = torch.tensor(vocab.group_full_ids(g)) if q_type == "constrained" else torch.arange(C)
+        sl = slice(g, S, vocab.n_attr) if q_type == "constrained" else slice(0, S)
+        lx = log_x0[:, sl][..., idx]                                       # (B,S',K)
+        tab = scheds[g]
+        tt = t.view(B, 1, 1)
+        lcat, lcbt = tab["log_cumprod_at"][tt], tab["log_cumprod_bt"][tt]
+        lcct, l1m = tab["log_cumprod_ct"][tt], tab["log_1_min_cumprod_ct"][tt]
+        logits = torch.cat([_log_add_exp(lx[..., :-1] + lcat, lcbt), _log_add_exp(lx[..., -1:] + l1m, lcct)], dim=-1)
+        k = (gumbel[:, sl][..., idx] + logits).argmax(dim=-1)
+        out[:, sl] = idx[k]
+    return out

@@ -256,3 +256,39 @@ def test_class_api_mirror():
     assert nxt.shape == (2, 155, 125)
     with pytest.raises(AssertionError):      # base.py:311
         core.sample(batch_size=1, sampling_cfg={"name": "random", "num_timesteps": 101})
+
+
+def test_q_sample_kernel_matches_oracle():
+    """forward (corruption) process on ids: bit-exact against the oracle under the shared noise contract"""
+    fx = Fixture("rico25_uncond_random")
+    eng = engine_for(fx)
+    v = fx.vocab
+    B = 16
+    g = torch.Generator().manual_seed(4)
+    x0 = torch.empty(B, v.S, dtype=torch.long)
+    for a in range(5):
+        ids = torch.tensor(v.group_full_ids(a)[:-1])
+        x0[:, a::5] = ids[torch.randint(0, len(ids), (B, 25), generator=g)]
+    t = torch.randint(0, 100, (B,), generator=g)
+    t[:3] = torch.tensor([0, 99, 50])
+    want = O.q_sample_ids(x0, t, 100, v, O.group_schedules(100, v), O.uniforms(21, 0, 2, 0, B, v.S, v.C))
+    got = eng.q_sample(x0.cuda(), t.cuda(), seed=21).cpu()
+    assert torch.equal(got, want)
+    shard = eng.q_sample(x0[8:].cuda(), t[8:].cuda(), seed=21, b_global0=8).cpu()     # keyed by the global layout index
+    assert torch.equal(shard, want[8:])
+
+
+def test_decode_kernel_matches_host_decode():
+    from layoutdm_b200 import Vocab, decode_ids, linear_centers
+    fx = Fixture("rico25_uncond_random")
+    eng = engine_for(fx)
+    g = torch.Generator().manual_seed(2)
+    ids = torch.randint(0, fx.vocab.C, (64, 125), generator=g)
+    ids[:8] = fx.ids_final.repeat(2, 1)[:8]
+    want = O.decode_ids(ids, fx.vocab)
+    got = {k: v.cpu() for k, v in eng.decode(ids.cuda()).items()}
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+    centers = torch.stack([torch.as_tensor(c, dtype=torch.float32) for c in linear_centers(32)])
+    got2 = {k: v.cpu() for k, v in eng.decode(ids.cuda(), centers).items()}
+    assert torch.allclose(got2["bbox"], want["bbox"], atol=1e-6) and torch.equal(got2["mask"], want["mask"])
