@@ -52,6 +52,7 @@ struct GemmParams {
   const float* ln_shift;  // [N]
   int adaln;
   float* out32;           // fp32 [M][N] normalised output (next residual, AdaLN case) or nullptr
+  int tile_sched;         // 1: spread single (row block, N tile) tiles over the CTA pairs (small batches); 0: a pair walks all N tiles of a row block
   int dbg;                // bring-up probe (env LDM_GEMM_DEBUG): 1 = skip the MMAs, 2 = skip the TMA operand loads; results are garbage
 };
 
@@ -115,6 +116,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t cta_rank = cluster_ctarank();               // 0 = leader
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int n_super = p.M / (2 * kBM);                       // 256-row blocks
+  // work units per pair: whole row blocks (inner loop over the N tiles) or, for small batches, single tiles
+  const int n_outer = p.tile_sched ? n_super * p.n_tiles : n_super, n_inner = p.tile_sched ? 1 : p.n_tiles;
   for (int i = threadIdx.x; i < p.N; i += kGemmThreads) {
     sbias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.0f;
     if constexpr (EPI == EPI_LN) {
@@ -143,8 +146,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== TMA producer (one thread in each CTA) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int sup = pair; sup < n_super; sup += n_pairs)
-      for (int n_blk = 0; n_blk < p.n_tiles; ++n_blk) {
+      for (int o = pair; o < n_outer; o += n_pairs)
+      for (int i = 0; i < n_inner; ++i) {
+        const int sup = p.tile_sched ? o / p.n_tiles : o, n_blk = p.tile_sched ? o % p.n_tiles : i;
         const int m_blk = 2 * sup + static_cast<int>(cta_rank);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -166,8 +170,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr uint32_t idesc = make_idesc_f16(2 * kBM, UMMA_N, BF16 ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int sup = pair; sup < n_super; sup += n_pairs)
-      for (int n_blk = 0; n_blk < p.n_tiles; ++n_blk) {
+      for (int o = pair; o < n_outer; o += n_pairs)
+      for (int i = 0; i < n_inner; ++i) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);              // both CTAs drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
@@ -228,8 +232,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     int acc = 0; uint32_t acc_phase = 0;
     if constexpr (EPI != EPI_LN) {
-      for (int sup = pair; sup < n_super; sup += n_pairs)
-      for (int n_blk = 0; n_blk < p.n_tiles; ++n_blk) {
+      for (int o = pair; o < n_outer; o += n_pairs)
+      for (int i = 0; i < n_inner; ++i) {
+        const int sup = p.tile_sched ? o / p.n_tiles : o, n_blk = p.tile_sched ? o % p.n_tiles : i;
         const int m_blk = 2 * sup + static_cast<int>(cta_rank);
         const int n0 = n_blk * BN_STORE;
         const int wrow0 = m_blk * kBM + quad * 32;

@@ -266,7 +266,10 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
   const int np = (n + 1) & ~1;            // layouts incl. the padding layout of an odd batch
   const int M = np * kBM;
   const int sms = h->num_sms & ~1;        // CTA pairs
-  auto pair_grid = [&](int) { return std::min(np, sms); };   // one CTA pair per 256-row block (it walks all N tiles of the block)
+  // large batches: one CTA pair per 256-row block (it walks all N tiles of the block); small batches: single tiles are
+  // spread over the pairs so that more than np/2 pairs have work (LN epilogues always need whole row blocks)
+  auto tile_sched = [&](int n_tiles) { return (n_tiles > 1 && np / 2 < sms / 2) ? 1 : 0; };
+  auto pair_grid = [&](int n_tiles) { return std::min(tile_sched(n_tiles) ? np * n_tiles : np, sms); };
   int done = 0;
   // test tap: stop after `debug_stop_after` launches
 #define LDM_STAGE_DONE() do { if (h->debug_stop_after && ++done >= h->debug_stop_after) { CK(cudaGetLastError()); return LDM_OK; } } while (0)
@@ -280,7 +283,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
   for (int l = 0; l < L; ++l) {
     {  // QKV projection (+bias, q * 1/sqrt(head_dim))
       GemmParams p{M, kQkvN, d, kQkvN / 256, h->bqkv[l], h->qkv16, kQkvN, 1.0f / sqrtf(static_cast<float>(d / h->desc.n_heads)), 8 * kHeadPad};
-      p.dbg = h->gemm_dbg;
+      p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles);
       ProfScope ps(h, CAT_QKV, st);
       gemm_tc_kernel<256, 256, 5, EPI_QKV, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 5, EPI_QKV>::kBytes, st>>>(
           h->m_x16, h->m_wqkv[l], h->b_qkv16, h->b_qkv16, h->b_qkv16, h->b_qkv16, p);
@@ -301,7 +304,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     LDM_STAGE_DONE();
     {  // FF1 + ReLU
       GemmParams p{M, ff, d, ff / kFF1Tile, h->b1[l], h->hid16, ff, 1.0f, 0};
-      p.dbg = h->gemm_dbg;
+      p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles);
       ProfScope ps(h, CAT_FF1, st);
       gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 5, EPI_RELU>::kBytes, st>>>(
           h->m_z16, h->m_w1[l], h->b_hid16, h->b_hid16, h->b_hid16, h->b_hid16, p);
