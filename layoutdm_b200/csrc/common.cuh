@@ -223,6 +223,11 @@ LDM_DEVINL void tmem_ld8(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+LDM_DEVINL uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
 // load `n` (8, 16 or 32; compile-time after unrolling) columns
 template <int N>
 LDM_DEVINL void tmem_ld(uint32_t taddr, uint32_t (&r)[32]) {
@@ -297,6 +302,12 @@ LDM_DEVINL uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 // u in (0,1): ((word >> 9) + 0.5) * 2^-23  (exact in fp32)
+LDM_DEVINL float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 LDM_DEVINL float u01_from_bits(uint32_t w) { return (static_cast<float>(w >> 9) + 0.5f) * 1.1920928955078125e-07f; }
 
 // explicit shared-space vector accesses (keeps them on the LDS/STS pipe; pointer arithmetic on the dynamic-smem base

@@ -291,7 +291,8 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     LDM_STAGE_DONE();
     {
       ProfScope ps(h, CAT_ATTN, st);
-      attention_kernel<BF16><<<std::min(np * h->desc.n_heads, 3 * h->num_sms), kAttThreads, kAttSmemBytes, st>>>(h->m_qkv16, h->m_att16, h->S, h->desc.n_heads, np);
+      attention_kernel<BF16><<<std::min(np * h->desc.n_heads, 2 * h->num_sms), kAttThreads, kAttSmemBytes, st>>>(h->m_qkv16, h->m_att16, h->S, h->desc.n_heads, np,
+                                                                                                                     d / h->desc.n_heads);
     }
     LDM_STAGE_DONE();
     {  // out-projection + bias + residual (from the NORMALISED x) -> y32 ; z16 = LayerNorm2(y)   [fused epilogue]
@@ -464,6 +465,8 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
     TRY(pack16(h, &h->wqkv[l], tmp, qmap_dev, kQkvN, d, d));
     std::vector<float> bq(kQkvN, 0.0f);
     for (int r = 0; r < kQkvN; ++r) if (qmap[r] >= 0) bq[r] = w->in_proj_b[static_cast<size_t>(l) * 3 * d + qmap[r]];
+    // column dh of every V head = 1 (zero weight row + unit bias): the attention kernel reads the softmax denominator from it
+    for (int hh = 0; hh < desc->n_heads; ++hh) bq[2 * 8 * kHeadPad + hh * kHeadPad + dh] = 1.0f;
     TRY(dev_upload(h, &h->bqkv[l], bq.data(), bq.size()));
     TRY(dev_upload(h, &tmp, w->out_proj_w + static_cast<size_t>(l) * d * d, static_cast<size_t>(d) * d));
     TRY(pack16(h, &h->wo[l], tmp, nullptr, d, kAttN, d, amap_dev));      // K = 512: head h occupies columns h*64 .. h*64+57
