@@ -108,6 +108,10 @@ LDM_DEVINL void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   // default semantics (.release.cta) like CUTLASS ClusterBarrier::arrive: a .release.cluster here costs MEMBAR.ALL.GPU per arrive
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
+// no memory ordering: for hand-offs whose data lives in TMEM (ordered by tcgen05.fence), saves the MEMBAR of a release
+LDM_DEVINL void mbar_arrive_cluster_relaxed(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 LDM_DEVINL void mbar_arrive_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes) : "memory");
 }

@@ -38,7 +38,7 @@ constexpr int kATileBytes = kBM * kBK * 2;   // 16 KB
 enum : int { EPI_QKV = 0, EPI_RELU = 1, EPI_F32 = 2, EPI_LN = 3 };
 
 struct GemmParams {
-  int M, N, K;            // M multiple of 256; N = n_tiles * BN_STORE
+  int M, N, K;            // M multiple of 256; N = n_tiles * BN_STORE, or (non-LN) a narrower last tile: N % BN_STORE a multiple of 32
   int n_tiles;
   const float* bias;      // [N] or nullptr
   void* out;              // remainder columns only: 16-bit [M][ldo] (QKV / RELU / LN out16) or float [M][ldo] (F32)
@@ -53,7 +53,7 @@ struct GemmParams {
   int adaln;
   float* out32;           // fp32 [M][N] normalised output (next residual, AdaLN case) or nullptr
   int tile_sched;         // 1: spread single (row block, N tile) tiles over the CTA pairs (small batches); 0: a pair walks all N tiles of a row block
-  int dbg;                // bring-up probe (env LDM_GEMM_DEBUG): 1 = skip the MMAs, 2 = skip the TMA operand loads; results are garbage
+  int dbg;                // bring-up probe (env LDM_GEMM_DEBUG), bit mask: 1 = skip the MMAs, 2 = skip the TMA operand loads, 4 = skip the epilogue body; results are garbage
 };
 
 template <int UMMA_N, int STAGES, int EPI>
@@ -93,11 +93,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   static_assert(UMMA_N % 16 == 0 && UMMA_N <= 256 && BN_STORE <= UMMA_N, "invalid UMMA shape");
   constexpr int kAccStride = 256;            // TMEM columns between the two accumulators
   constexpr uint32_t kTmemCols = 512;
-  constexpr int kHalfRows = UMMA_N / 2;
   constexpr int kFull = BN_STORE / 32, kRem = BN_STORE % 32;
   constexpr int kSplit = (kFull + 1) / 2;    // half 0: 32-col chunks [0, kSplit), half 1: [kSplit, kFull) + remainder
   static_assert(kRem == 0 || kRem == 8, "unsupported tile width");
-  static_assert(EPI != EPI_LN || (BN_STORE == 232), "LN epilogue is laid out for 2 x 232 columns");
+  static_assert(EPI != EPI_LN || (BN_STORE == 224 && UMMA_N == 240), "LN epilogue is laid out for 464 = 224 + 240 columns");
+  static_assert(EPI == EPI_LN || BN_STORE == UMMA_N, "plain epilogues store whole UMMA tiles");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -150,15 +150,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int i = 0; i < n_inner; ++i) {
         const int sup = p.tile_sched ? o / p.n_tiles : o, n_blk = p.tile_sched ? o % p.n_tiles : i;
         const int m_blk = 2 * sup + static_cast<int>(cta_rank);
+        // weight rows per CTA (the TMA box stays UMMA_N / 2 rows: rows past b_half are unused)
+        const int b_half = (EPI == EPI_LN ? (n_blk == 0 ? BN_STORE : UMMA_N) : min(UMMA_N, p.N - n_blk * BN_STORE)) / 2;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * SM::kStageBytes;
           const uint32_t lead_full = mapa_shared(smem_u32(&full[stage]), 0);
-          if (p.dbg >= 2) { mbar_arrive_cluster(lead_full); }
+          if (p.dbg & 2) { mbar_arrive_cluster(lead_full); }
           else {
           mbar_arrive_expect_tx_cluster(lead_full, SM::kStageBytes);
           tma_load_2d_2cta(sa, &map_a, lead_full, kb * kBK, m_blk * kBM);
-          tma_load_2d_2cta(sa + kATileBytes, &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * kHalfRows);
+          tma_load_2d_2cta(sa + kATileBytes, &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * b_half);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -172,6 +174,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int acc = 0; uint32_t acc_phase = 0;
       for (int o = pair; o < n_outer; o += n_pairs)
       for (int i = 0; i < n_inner; ++i) {
+        const int n_blk_mma = p.tile_sched ? o % p.n_tiles : i;
+        const int nw = EPI == EPI_LN ? (n_blk_mma == 0 ? BN_STORE : UMMA_N) : min(UMMA_N, p.N - n_blk_mma * BN_STORE);   // last tile may be narrower
+        const uint32_t idesc_t = nw == UMMA_N ? idesc : make_idesc_f16(2 * kBM, nw, BF16 ? 1 : 0);
         mbar_wait(&tempty[acc], acc_phase ^ 1);              // both CTAs drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
@@ -182,9 +187,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint64_t da = make_smem_desc_sw128(sa);
           const uint64_t db = make_smem_desc_sw128(sa + kATileBytes);
           const int nk = min(kBK, p.K - kb * kBK) / kUmmaK;     // K tail: TMA zero-fills, skip the zero k-steps
-          if (p.dbg != 1)
+          if (!(p.dbg & 1))
           for (int k = 0; k < nk; ++k)
-            umma_f16_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);   // +32 B per k-step (>>4 = 2)
+            umma_f16_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc_t, (kb | k) != 0);   // +32 B per k-step (>>4 = 2)
           umma_commit_2cta_mc(&empty[stage], static_cast<uint16_t>(0b11));       // free the stage in both CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -243,8 +248,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + tlane + acc * kAccStride;
+        int cb = c_begin, ce = c_end;
+        if (n0 + BN_STORE > p.N) {                   // narrower last tile: split its 32-column chunks over the two halves
+          const int nc = (p.N - n0) / 32;
+          cb = half == 0 ? 0 : nc / 2; ce = half == 0 ? nc / 2 : nc;
+        }
+        if (p.dbg & 4) ce = cb;
 #pragma unroll 1
-        for (int c = c_begin; c < (p.dbg == 3 ? c_begin : c_end); ++c) {
+        for (int c = cb; c < ce; ++c) {
           const int c0 = c * 32;
           uint32_t r[32];
           tmem_ld<32>(taddr + c0, r);
@@ -296,26 +307,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));   // leader's barrier: 8 warps x 2 CTAs
+        if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty[acc]), 0));   // leader's barrier: 8 warps x 2 CTAs
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     } else {
       // ============ fused residual + LayerNorm epilogue (out-projection / FF2) ============
-      // One CTA owns 128 complete rows: both 232-column tiles of its row block run back to back on this pair.
+      // One CTA owns 128 complete rows: the two column tiles of its row block (224 + 240 = 464) run back to back on this
+      // pair.  Every 32-column chunk goes through TMA (the last chunk of tile 1 covers columns 448..479: the TMA load
+      // zero-fills and the TMA stores clip the 16 columns past N, the statistics mask them).
       float2* sstat = reinterpret_cast<float2*>(smem + SM::kOffStat);
       const uint32_t sgamma_addr = sbias_addr + p.N * 4, sbeta_addr = sbias_addr + 2 * p.N * 4;
       const uint32_t lbuf = wbuf + 6144;                     // residual block, rows of 128 B (128B swizzle)
       uint8_t* lbuf_ptr = smem + SM::kOffStaging + we * SM::kWarpStage + 6144;
       uint64_t* lbar = &lbars[we];
       uint32_t lphase = 0;
+      const float inv_n = 1.0f / static_cast<float>(p.N);
       for (int sup = pair; sup < n_super; sup += n_pairs) {
         const int m_blk = 2 * sup + static_cast<int>(cta_rank);
-        const size_t row = static_cast<size_t>(m_blk) * kBM + row_in_tile;
         const int wrow0 = m_blk * kBM + quad * 32;            // first row of this warp
         float sum = 0.0f, sq = 0.0f;
         // ---------------- phase A ----------------
         for (int n_blk = 0; n_blk < 2; ++n_blk) {
           const int n0 = n_blk * BN_STORE;
+          const int ce = (p.dbg & 4) ? c_begin : (half == 0 ? kSplit : kFull + n_blk);   // tile 1 has one more (half-valid) chunk
           const uint32_t taddr = tmem_base + tlane + n_blk * kAccStride;
           auto issue_resid = [&](int c0) {                    // async: 32 rows x 32 fp32 of the residual -> lbuf
             if (lane == 0) {
@@ -323,20 +337,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tma_load_2d(lbuf_ptr, &map_resid, lbar, n0 + c0, wrow0);
             }
           };
-          issue_resid(c_begin * 32);                          // in flight while the MMAs of this tile still run
-          float rem_res[8];
-          if (half == 1) {                                    // remainder columns 224..231: direct (also early)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const float4 rs = __ldg(reinterpret_cast<const float4*>(p.resid + row * p.N + n0 + kFull * 32) + j);
-              rem_res[4 * j] = rs.x; rem_res[4 * j + 1] = rs.y; rem_res[4 * j + 2] = rs.z; rem_res[4 * j + 3] = rs.w;
-            }
-          }
+          if (c_begin < ce) issue_resid(c_begin * 32);        // in flight while the MMAs of this tile still run
           mbar_wait(&tfull[n_blk], acc_phase);
           tc_fence_after();
 #pragma unroll 1
-          for (int c = c_begin; c < c_end; ++c) {
+          for (int c = c_begin; c < ce; ++c) {
             const int c0 = c * 32;
+            const int n_ok = p.N - (n0 + c0);                 // >= 32 except for the last chunk of the row (16)
             uint32_t r[32];
             tmem_ld<32>(taddr + c0, r);
             mbar_wait(lbar, lphase); lphase ^= 1;             // residual block has landed
@@ -348,43 +355,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               y[4 * j] = rs.x + b4.x; y[4 * j + 1] = rs.y + b4.y; y[4 * j + 2] = rs.z + b4.z; y[4 * j + 3] = rs.w + b4.w;
             }
             __syncwarp();                                     // every lane is done reading lbuf
-            if (c + 1 < c_end) issue_resid(c0 + 32);          // next block streams in during the math / stores below
+            if (c + 1 < ce) issue_resid(c0 + 32);             // next block streams in during the math / stores below
             tmem_wait_ld();
+            if (n_ok >= 32) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              y[j] += __uint_as_float(r[j]);
-              sum += y[j];
-              sq = fmaf(y[j], y[j], sq);
-              r[j] = __float_as_uint(y[j]);
+              for (int j = 0; j < 32; ++j) {
+                y[j] += __uint_as_float(r[j]);
+                sum += y[j];
+                sq = fmaf(y[j], y[j], sq);
+                r[j] = __float_as_uint(y[j]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                y[j] = j < n_ok ? y[j] + __uint_as_float(r[j]) : 0.0f;
+                sum += y[j];
+                sq = fmaf(y[j], y[j], sq);
+                r[j] = __float_as_uint(y[j]);
+              }
             }
             tmem_st<32>(taddr + c0, r);
             if (p.y_out != nullptr) store_f32(&map_yout, y, n0 + c0, wrow0);
-          }
-          if (half == 1) {
-            const int c0 = kFull * 32;
-            uint32_t r[32];
-            tmem_ld<8>(taddr + c0, r);
-            float y[8];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const float4 b4 = lds_f4(sbias_addr + (n0 + c0 + 4 * j) * 4);
-              y[4 * j] = rem_res[4 * j] + b4.x; y[4 * j + 1] = rem_res[4 * j + 1] + b4.y;
-              y[4 * j + 2] = rem_res[4 * j + 2] + b4.z; y[4 * j + 3] = rem_res[4 * j + 3] + b4.w;
-            }
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              y[j] += __uint_as_float(r[j]);
-              sum += y[j];
-              sq = fmaf(y[j], y[j], sq);
-              r[j] = __float_as_uint(y[j]);
-            }
-            tmem_st<8>(taddr + c0, r);
-            if (p.y_out != nullptr) {
-              float4* dst = reinterpret_cast<float4*>(p.y_out + row * p.N + n0 + c0);
-              dst[0] = make_float4(y[0], y[1], y[2], y[3]);
-              dst[1] = make_float4(y[4], y[5], y[6], y[7]);
-            }
           }
         }
         // ---------------- row statistics across the two column halves ----------------
@@ -392,12 +383,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tmem_wait_st();
         named_bar_sync(1, kEpiThreads);
         const float2 other = sstat[(half ^ 1) * kBM + row_in_tile];
-        const float mean = (sum + other.x) * (1.0f / (2 * BN_STORE));
-        const float var = fmaxf((sq + other.y) * (1.0f / (2 * BN_STORE)) - mean * mean, 0.0f);
+        const float mean = (sum + other.x) * inv_n;
+        const float var = fmaxf((sq + other.y) * inv_n - mean * mean, 0.0f);
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
         // ---------------- phase B ----------------
         for (int n_blk = 0; n_blk < 2; ++n_blk) {
           const int n0 = n_blk * BN_STORE;
+          const int ce = (p.dbg & 4) ? c_begin : (half == 0 ? kSplit : kFull + n_blk);
           const uint32_t taddr = tmem_base + tlane + n_blk * kAccStride;
           auto norm4 = [&](const uint32_t* rr4, int col, float* o) {
             const float4 g4 = lds_f4(sgamma_addr + col * 4), h4 = lds_f4(sbeta_addr + col * 4);
@@ -407,7 +399,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             o[3] = (__uint_as_float(rr4[3]) - mean) * rstd * g4.w + h4.w;
           };
 #pragma unroll 1
-          for (int c = c_begin; c < c_end; ++c) {
+          for (int c = c_begin; c < ce; ++c) {
             const int c0 = c * 32;
             uint32_t r[32];
             tmem_ld<32>(taddr + c0, r);
@@ -418,25 +410,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             store_16(&map_out, v, n0 + c0, wrow0);
             if (p.out32 != nullptr) store_f32(&map_out32, v, n0 + c0, wrow0);
           }
-          if (half == 1) {
-            const int c0 = kFull * 32;
-            uint32_t r[32];
-            tmem_ld<8>(taddr + c0, r);
-            tmem_wait_ld();
-            float v[8];
-            norm4(r, n0 + c0, v);
-            norm4(r + 4, n0 + c0 + 4, v + 4);
-            *reinterpret_cast<uint4*>(static_cast<typename O::T*>(p.out) + row * p.N + n0 + c0) =
-                make_uint4(O::pack(v[0], v[1]), O::pack(v[2], v[3]), O::pack(v[4], v[5]), O::pack(v[6], v[7]));
-            if (p.out32 != nullptr) {
-              float4* dst = reinterpret_cast<float4*>(p.out32 + row * p.N + n0 + c0);
-              dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-              dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-            }
-          }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[n_blk]), 0));   // release this accumulator
+          if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty[n_blk]), 0));   // release this accumulator
         }
         acc_phase ^= 1;
       }

@@ -299,15 +299,15 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       GemmParams p{M, d, kAttN, d / kFF1Tile, h->bo[l], h->z16, d, 1.0f, 0, h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr};
       p.dbg = h->gemm_dbg;
       ProfScope ps(h, CAT_OUTPROJ, st);
-      gemm_tc_kernel<kFF1Tile, 240, 4, EPI_LN, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<240, 4, EPI_LN>::kBytes, st>>>(
+      gemm_tc_kernel<224, 240, 4, EPI_LN, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<240, 4, EPI_LN>::kBytes, st>>>(
           h->m_att16, h->m_wo[l], h->b_z16, h->b_x32, h->b_y32, h->b_y32, p);
     }
     LDM_STAGE_DONE();
     {  // FF1 + ReLU
-      GemmParams p{M, ff, d, ff / kFF1Tile, h->b1[l], h->hid16, ff, 1.0f, 0};
+      GemmParams p{M, ff, d, (ff + 255) / 256, h->b1[l], h->hid16, ff, 1.0f, 0};   // 7 tiles of 256 columns + one of 64
       p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles);
       ProfScope ps(h, CAT_FF1, st);
-      gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<240, 5, EPI_RELU>::kBytes, st>>>(
+      gemm_tc_kernel<256, 256, 5, EPI_RELU, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 5, EPI_RELU>::kBytes, st>>>(
           h->m_z16, h->m_w1[l], h->b_hid16, h->b_hid16, h->b_hid16, h->b_hid16, p);
     }
     LDM_STAGE_DONE();
@@ -322,7 +322,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       }
       p.dbg = h->gemm_dbg;
       ProfScope ps(h, CAT_FF2, st);
-      gemm_tc_kernel<kFF1Tile, 240, 4, EPI_LN, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<240, 4, EPI_LN>::kBytes, st>>>(
+      gemm_tc_kernel<224, 240, 4, EPI_LN, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<240, 4, EPI_LN>::kBytes, st>>>(
           h->m_hid16, h->m_w2[l], *mo, h->b_y32, h->b_x32, h->b_x32, p);
     }
     LDM_STAGE_DONE();
@@ -481,7 +481,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
     TRY(dev_upload(h, &h->ln2b[l], w->norm2_b + static_cast<size_t>(l) * d, static_cast<size_t>(d)));
     TRY(make_map(&h->m_wqkv[l], h->wqkv[l], kQkvN, d, 128, h->bf16));   // each CTA of a pair loads half of the weight tile
     TRY(make_map(&h->m_wo[l], h->wo[l], d, kAttN, 120, h->bf16));
-    TRY(make_map(&h->m_w1[l], h->w1[l], ff, d, 120, h->bf16));
+    TRY(make_map(&h->m_w1[l], h->w1[l], ff, d, 128, h->bf16));
     TRY(make_map(&h->m_w2[l], h->w2[l], d, ff, 120, h->bf16));
   }
   {
@@ -506,15 +506,15 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
 
   if (h->bf16) {
     TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, true>, GemmSmem<256, 5, EPI_QKV>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, true>, GemmSmem<240, 5, EPI_RELU>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_RELU, true>, GemmSmem<256, 5, EPI_RELU>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, true>, GemmSmem<160, 5, EPI_F32>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 4, EPI_LN, true>, GemmSmem<240, 4, EPI_LN>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<224, 240, 4, EPI_LN, true>, GemmSmem<240, 4, EPI_LN>::kBytes)));
     TRY((set_smem(attention_kernel<true>, kAttSmemBytes)));
   } else {
     TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, false>, GemmSmem<256, 5, EPI_QKV>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 5, EPI_RELU, false>, GemmSmem<240, 5, EPI_RELU>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_RELU, false>, GemmSmem<256, 5, EPI_RELU>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, false>, GemmSmem<160, 5, EPI_F32>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<kFF1Tile, 240, 4, EPI_LN, false>, GemmSmem<240, 4, EPI_LN>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<224, 240, 4, EPI_LN, false>, GemmSmem<240, 4, EPI_LN>::kBytes)));
     TRY((set_smem(attention_kernel<false>, kAttSmemBytes)));
   }
 #undef TRY
