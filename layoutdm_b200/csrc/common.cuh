@@ -274,6 +274,28 @@ LDM_DEVINL void tmem_st(uint32_t taddr, const uint32_t (&r)[32]) {
   else tmem_st8(taddr, r);
 }
 // named barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
+// global-memory flag hand-off between co-resident CTAs
+LDM_DEVINL void st_release_gpu_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+LDM_DEVINL unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// 8-byte {fp32 payload, 32-bit epoch} words: payload and flag travel in one single-copy-atomic access (no fences needed)
+LDM_DEVINL void st_ll_word(unsigned long long* p, float v, unsigned epoch) {
+  const unsigned long long w = (static_cast<unsigned long long>(epoch) << 32) | __float_as_uint(v);
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+LDM_DEVINL unsigned long long ld_ll_word(const unsigned long long* p) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
+}
+LDM_DEVINL float2 ld_cg_f2(const float2* p) {
+  float2 v;
+  asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
 LDM_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------------------

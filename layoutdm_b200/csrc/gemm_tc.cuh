@@ -52,6 +52,9 @@ struct GemmParams {
   const float* ln_shift;  // [N]
   int adaln;
   float* out32;           // fp32 [M][N] normalised output (next residual, AdaLN case) or nullptr
+  // EPI_LN row statistics exchanged between the two CTA pairs that hold the two column tiles of a row block
+  unsigned long long* ln_stats;   // [n_units * 2 CTAs][128 rows][2] {fp32 partial, launch epoch} words: sum and sum of squares over a unit's columns
+  unsigned ln_epoch;
   int tile_sched;         // 1: spread single (row block, N tile) tiles over the CTA pairs (small batches); 0: a pair walks all N tiles of a row block
   int dbg;                // bring-up probe (env LDM_GEMM_DEBUG), bit mask: 1 = skip the MMAs, 2 = skip the TMA operand loads, 4 = skip the epilogue body; results are garbage
 };
@@ -67,7 +70,7 @@ struct GemmSmem {
   static constexpr int kStagingBytes = 8 * kWarpStage;
   static constexpr int kBarBytes = 256;
   static constexpr int kBiasBytes = 1856 * 4;   // bias (and, for LN, gamma / beta) vectors of the layer
-  static constexpr int kStatBytes = 2 * kBM * 8;  // LN: per-row (sum, sumsq) partials of the two column halves
+  static constexpr int kStatBytes = 4 * kBM * 8;  // LN: per-row (sum, sumsq) partials of the two column halves, per accumulator
   static constexpr int kOffStaging = STAGES * kStageBytes;
   static constexpr int kOffBars = kOffStaging + kStagingBytes;
   static constexpr int kOffBias = kOffBars + kBarBytes;
@@ -312,9 +315,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     } else {
       // ============ fused residual + LayerNorm epilogue (out-projection / FF2) ============
-      // One CTA owns 128 complete rows: the two column tiles of its row block (224 + 240 = 464) run back to back on this
-      // pair.  Every 32-column chunk goes through TMA (the last chunk of tile 1 covers columns 448..479: the TMA load
-      // zero-fills and the TMA stores clip the 16 columns past N, the statistics mask them).
+      // Work unit = (256-row block, column tile): tile 0 = columns [0, 224), tile 1 = [224, 464).  The two tiles of a row
+      // block run at the same time on two neighbouring CTA pairs (units o and o ^ 1; the launch keeps every pair resident
+      // and the pair count even), so a CTA holds 128 rows x <= 240 accumulator columns, the accumulators are double
+      // buffered and this epilogue overlaps the MMAs of the pair's next unit.  LayerNorm needs whole rows: each CTA
+      // publishes per-row (sum, sum of squares) partials of its tile through global memory and picks up its partner's.
+      //   phase A  y = acc + bias + resid -> back into TMEM (+ y_out), row partials
+      //   exchange with the partner CTA (same rows, other tile)
+      //   phase B  normalise from TMEM, 16-bit (+ fp32) outputs; release the accumulator
+      // Every 32-column chunk goes through TMA (the last chunk of tile 1 covers columns 448..479: the TMA load zero-fills
+      // and the TMA stores clip the 16 columns past N, the statistics mask them).
       float2* sstat = reinterpret_cast<float2*>(smem + SM::kOffStat);
       const uint32_t sgamma_addr = sbias_addr + p.N * 4, sbeta_addr = sbias_addr + 2 * p.N * 4;
       const uint32_t lbuf = wbuf + 6144;                     // residual block, rows of 128 B (128B swizzle)
@@ -322,23 +332,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint64_t* lbar = &lbars[we];
       uint32_t lphase = 0;
       const float inv_n = 1.0f / static_cast<float>(p.N);
-      for (int sup = pair; sup < n_super; sup += n_pairs) {
+      for (int o = pair; o < n_outer; o += n_pairs) {
+        const int sup = o >> 1, n_blk = o & 1;
         const int m_blk = 2 * sup + static_cast<int>(cta_rank);
         const int wrow0 = m_blk * kBM + quad * 32;            // first row of this warp
+        const int n0 = n_blk * BN_STORE;
+        const int ce = (p.dbg & 4) ? c_begin : (half == 0 ? kSplit : kFull + n_blk);   // tile 1 has one more (half-valid) chunk
+        const uint32_t taddr = tmem_base + tlane + acc * kAccStride;
         float sum = 0.0f, sq = 0.0f;
         // ---------------- phase A ----------------
-        for (int n_blk = 0; n_blk < 2; ++n_blk) {
-          const int n0 = n_blk * BN_STORE;
-          const int ce = (p.dbg & 4) ? c_begin : (half == 0 ? kSplit : kFull + n_blk);   // tile 1 has one more (half-valid) chunk
-          const uint32_t taddr = tmem_base + tlane + n_blk * kAccStride;
+        {
           auto issue_resid = [&](int c0) {                    // async: 32 rows x 32 fp32 of the residual -> lbuf
             if (lane == 0) {
               mbar_arrive_expect_tx(lbar, 4096);
               tma_load_2d(lbuf_ptr, &map_resid, lbar, n0 + c0, wrow0);
             }
           };
-          if (c_begin < ce) issue_resid(c_begin * 32);        // in flight while the MMAs of this tile still run
-          mbar_wait(&tfull[n_blk], acc_phase);
+          if (c_begin < ce) issue_resid(c_begin * 32);        // in flight while the MMAs of this unit still run
+          mbar_wait(&tfull[acc], acc_phase);
           tc_fence_after();
 #pragma unroll 1
           for (int c = c_begin; c < ce; ++c) {
@@ -378,25 +389,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (p.y_out != nullptr) store_f32(&map_yout, y, n0 + c0, wrow0);
           }
         }
-        // ---------------- row statistics across the two column halves ----------------
-        sstat[half * kBM + row_in_tile] = make_float2(sum, sq);
+        // ---------------- row statistics: the two column halves of this CTA, then the partner's tile ----------------
+        sstat[(acc * 2 + half) * kBM + row_in_tile] = make_float2(sum, sq);
         tmem_wait_st();
         named_bar_sync(1, kEpiThreads);
-        const float2 other = sstat[(half ^ 1) * kBM + row_in_tile];
-        const float mean = (sum + other.x) * inv_n;
-        const float var = fmaxf((sq + other.y) * inv_n - mean * mean, 0.0f);
+        const float2 other = sstat[(acc * 2 + (half ^ 1)) * kBM + row_in_tile];
+        sum += other.x; sq += other.y;
+        // {value, epoch} words: row r of CTA slot s lives at ln_stats[(s * 128 + r) * 2 + {0: sum, 1: sum of squares}]
+        unsigned long long* my_w = p.ln_stats + ((static_cast<size_t>(o) * 2 + cta_rank) * kBM + row_in_tile) * 2;
+        const unsigned long long* peer_w = p.ln_stats + ((static_cast<size_t>(o ^ 1) * 2 + cta_rank) * kBM + row_in_tile) * 2;
+        if (half == 0) { st_ll_word(my_w, sum, p.ln_epoch); st_ll_word(my_w + 1, sq, p.ln_epoch); }
+        float2 peer;
+        {
+          unsigned long long w0, w1;
+          uint32_t spins = 0;
+          do {
+            w0 = ld_ll_word(peer_w); w1 = ld_ll_word(peer_w + 1);
+            if (++spins > (1u << 24)) { printf("LN statistics exchange timed out (unit %d)\n", o); __trap(); }
+          } while (static_cast<unsigned>(w0 >> 32) != p.ln_epoch || static_cast<unsigned>(w1 >> 32) != p.ln_epoch);
+          peer = make_float2(__uint_as_float(static_cast<unsigned>(w0)), __uint_as_float(static_cast<unsigned>(w1)));
+        }
+        const float mean = (sum + peer.x) * inv_n;
+        const float var = fmaxf((sq + peer.y) * inv_n - mean * mean, 0.0f);
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
         // ---------------- phase B ----------------
-        for (int n_blk = 0; n_blk < 2; ++n_blk) {
-          const int n0 = n_blk * BN_STORE;
-          const int ce = (p.dbg & 4) ? c_begin : (half == 0 ? kSplit : kFull + n_blk);
-          const uint32_t taddr = tmem_base + tlane + n_blk * kAccStride;
-          auto norm4 = [&](const uint32_t* rr4, int col, float* o) {
+        {
+          auto norm4 = [&](const uint32_t* rr4, int col, float* ov) {
             const float4 g4 = lds_f4(sgamma_addr + col * 4), h4 = lds_f4(sbeta_addr + col * 4);
-            o[0] = (__uint_as_float(rr4[0]) - mean) * rstd * g4.x + h4.x;
-            o[1] = (__uint_as_float(rr4[1]) - mean) * rstd * g4.y + h4.y;
-            o[2] = (__uint_as_float(rr4[2]) - mean) * rstd * g4.z + h4.z;
-            o[3] = (__uint_as_float(rr4[3]) - mean) * rstd * g4.w + h4.w;
+            ov[0] = (__uint_as_float(rr4[0]) - mean) * rstd * g4.x + h4.x;
+            ov[1] = (__uint_as_float(rr4[1]) - mean) * rstd * g4.y + h4.y;
+            ov[2] = (__uint_as_float(rr4[2]) - mean) * rstd * g4.z + h4.z;
+            ov[3] = (__uint_as_float(rr4[3]) - mean) * rstd * g4.w + h4.w;
           };
 #pragma unroll 1
           for (int c = c_begin; c < ce; ++c) {
@@ -412,9 +435,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty[n_blk]), 0));   // release this accumulator
+          if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty[acc]), 0));   // release this accumulator
         }
-        acc_phase ^= 1;
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
     if (lane == 0) bulk_wait_all();            // this warp's TMA stores have completed before the CTA retires

@@ -129,6 +129,7 @@ struct LdmHandle {
   int cap = 0;
   void *x16 = nullptr, *qkv16 = nullptr, *att16 = nullptr, *z16 = nullptr, *hid16 = nullptr;
   float *x32 = nullptr, *y32 = nullptr, *logits = nullptr;
+  unsigned long long* ln_stats = nullptr; unsigned ln_epoch = 0;   // LN statistics exchange between CTA pairs (gemm_tc.cuh)
   long long* ids[2] = {nullptr, nullptr};
   long long* ids_final = nullptr;
   long long *c_seq = nullptr, *c_seq_orig = nullptr; unsigned char* c_mask = nullptr; float* c_tbl = nullptr;  // staging for ldm_sample_host
@@ -219,7 +220,7 @@ int ensure_workspace(LdmHandle* h, int n_layouts) {
   n_layouts = (n_layouts + 1) & ~1;     // GEMM CTA pairs work on 256-row blocks: keep an even number of layout tiles
   if (n_layouts <= h->cap) return LDM_OK;
   // free the old workspace
-  void* olds[] = {h->x16, h->qkv16, h->att16, h->z16, h->hid16, h->x32, h->y32, h->logits, h->ids[0], h->ids[1], h->ids_final, h->c_seq, h->c_seq_orig, h->c_mask};
+  void* olds[] = {h->x16, h->qkv16, h->att16, h->z16, h->hid16, h->x32, h->y32, h->logits, h->ids[0], h->ids[1], h->ids_final, h->c_seq, h->c_seq_orig, h->c_mask, h->ln_stats};
   for (void* p : olds) if (p) cudaFree(p);
   const size_t M = static_cast<size_t>(n_layouts) * kBM;
   const int d = h->desc.d_model, ff = h->desc.d_ff;
@@ -238,6 +239,9 @@ int ensure_workspace(LdmHandle* h, int n_layouts) {
   CK(cudaMalloc(reinterpret_cast<void**>(&h->c_seq), nid * 8));
   CK(cudaMalloc(reinterpret_cast<void**>(&h->c_seq_orig), nid * 8));
   CK(cudaMalloc(reinterpret_cast<void**>(&h->c_mask), nid));
+  CK(cudaMalloc(reinterpret_cast<void**>(&h->ln_stats), static_cast<size_t>(n_layouts) * 2 * kBM * 2 * sizeof(unsigned long long)));
+  CK(cudaMemset(h->ln_stats, 0, static_cast<size_t>(n_layouts) * 2 * kBM * 2 * sizeof(unsigned long long)));
+  h->ln_epoch = 0;
   // zero once: the padding layout (odd batch sizes) and the 3 padding rows of every layout tile must stay finite
   CK(cudaMemset(h->x16, 0, M * d * 2)); CK(cudaMemset(h->qkv16, 0, M * kQkvN * 2)); CK(cudaMemset(h->att16, 0, M * kAttN * 2));
   CK(cudaMemset(h->z16, 0, M * d * 2)); CK(cudaMemset(h->hid16, 0, M * ff * 2)); CK(cudaMemset(h->x32, 0, M * d * 4));
@@ -270,6 +274,8 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
   // spread over the pairs so that more than np/2 pairs have work (LN epilogues always need whole row blocks)
   auto tile_sched = [&](int n_tiles) { return (n_tiles > 1 && np / 2 < sms / 2) ? 1 : 0; };
   auto pair_grid = [&](int n_tiles) { return std::min(tile_sched(n_tiles) ? np * n_tiles : np, sms); };
+  // LN GEMMs: units (row block, column tile) on neighbouring pairs -> an even number of pairs, all of them resident
+  const int ln_grid = std::min(2 * np, h->num_sms) & ~3;
   int done = 0;
   // test tap: stop after `debug_stop_after` launches
 #define LDM_STAGE_DONE() do { if (h->debug_stop_after && ++done >= h->debug_stop_after) { CK(cudaGetLastError()); return LDM_OK; } } while (0)
@@ -297,9 +303,9 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     LDM_STAGE_DONE();
     {  // out-projection + bias + residual (from the NORMALISED x) -> y32 ; z16 = LayerNorm2(y)   [fused epilogue]
       GemmParams p{M, d, kAttN, d / kFF1Tile, h->bo[l], h->z16, d, 1.0f, 0, h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr};
-      p.dbg = h->gemm_dbg;
+      p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch;
       ProfScope ps(h, CAT_OUTPROJ, st);
-      gemm_tc_kernel<224, 240, 4, EPI_LN, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<240, 4, EPI_LN>::kBytes, st>>>(
+      gemm_tc_kernel<224, 240, 4, EPI_LN, BF16><<<ln_grid, kGemmThreads, GemmSmem<240, 4, EPI_LN>::kBytes, st>>>(
           h->m_att16, h->m_wo[l], h->b_z16, h->b_x32, h->b_y32, h->b_y32, p);
     }
     LDM_STAGE_DONE();
@@ -320,9 +326,9 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       } else {
         p.ln_scale = h->hlnw; p.ln_shift = h->hlnb; p.adaln = 0; p.out32 = nullptr; p.out = h->z16;
       }
-      p.dbg = h->gemm_dbg;
+      p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch;
       ProfScope ps(h, CAT_FF2, st);
-      gemm_tc_kernel<224, 240, 4, EPI_LN, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<240, 4, EPI_LN>::kBytes, st>>>(
+      gemm_tc_kernel<224, 240, 4, EPI_LN, BF16><<<ln_grid, kGemmThreads, GemmSmem<240, 4, EPI_LN>::kBytes, st>>>(
           h->m_hid16, h->m_w2[l], *mo, h->b_y32, h->b_x32, h->b_x32, p);
     }
     LDM_STAGE_DONE();
