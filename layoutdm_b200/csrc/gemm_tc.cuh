@@ -109,10 +109,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* empty = bars + STAGES;           // per CTA: released by the leader's multicast tcgen05.commit
   uint64_t* tfull = bars + 2 * STAGES;       // per CTA: accumulator ready (multicast commit)
   uint64_t* tempty = bars + 2 * STAGES + 2;  // leader's copy: 16 warp arrivals (8 epilogue warps x 2 CTAs)
-  uint64_t* lbars = bars + 2 * STAGES + 4;   // LN: one residual-load barrier per epilogue warp
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
+  uint64_t* lbars = bars + 2 * STAGES + 4;   // LN: two residual-load barriers per epilogue warp
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 20);
   float* sbias = reinterpret_cast<float*>(smem + SM::kOffBias);
-  static_assert((2 * STAGES + 12) * 8 + 4 <= SM::kBarBytes, "barrier block overflow");
+  static_assert((2 * STAGES + 20) * 8 + 4 <= SM::kBarBytes, "barrier block overflow");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + kBK - 1) / kBK;
@@ -135,7 +135,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tma_prefetch_desc(&map_out);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }
-    for (int i = 0; i < 8; ++i) mbar_init(&lbars[i], 1);
+    for (int i = 0; i < 16; ++i) mbar_init(&lbars[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2cta(tmem_ptr, kTmemCols);
@@ -327,10 +327,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // and the TMA stores clip the 16 columns past N, the statistics mask them).
       float2* sstat = reinterpret_cast<float2*>(smem + SM::kOffStat);
       const uint32_t sgamma_addr = sbias_addr + p.N * 4, sbeta_addr = sbias_addr + 2 * p.N * 4;
-      const uint32_t lbuf = wbuf + 6144;                     // residual block, rows of 128 B (128B swizzle)
-      uint8_t* lbuf_ptr = smem + SM::kOffStaging + we * SM::kWarpStage + 6144;
-      uint64_t* lbar = &lbars[we];
-      uint32_t lphase = 0;
+      // residual blocks (rows of 128 B, 128B swizzle): buffer 0 is private; without a y_out stream (FF2) the fp32 store
+      // staging block is idle during phase A and serves as a second buffer, i.e. the loads run two chunks ahead
+      const int n_lbuf = p.y_out != nullptr ? 1 : 2;
+      const uint32_t lbuf_off[2] = {6144u, 0u};
+      uint8_t* const wbuf_ptr = smem + SM::kOffStaging + we * SM::kWarpStage;
+      uint64_t* lbar = &lbars[2 * we];
+      uint32_t lphase = 0;                                   // one phase bit per buffer
       const float inv_n = 1.0f / static_cast<float>(p.N);
       for (int o = pair; o < n_outer; o += n_pairs) {
         const int sup = o >> 1, n_blk = o & 1;
@@ -342,13 +345,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float sum = 0.0f, sq = 0.0f;
         // ---------------- phase A ----------------
         {
-          auto issue_resid = [&](int c0) {                    // async: 32 rows x 32 fp32 of the residual -> lbuf
-            if (lane == 0) {
-              mbar_arrive_expect_tx(lbar, 4096);
-              tma_load_2d(lbuf_ptr, &map_resid, lbar, n0 + c0, wrow0);
+          auto issue_resid = [&](int c) {                     // async: 32 rows x 32 fp32 of the residual -> buffer (c - c_begin) % n_lbuf
+            if (lane == 0 && c < ce) {
+              const int b = (c - c_begin) % n_lbuf;
+              mbar_arrive_expect_tx(&lbar[b], 4096);
+              tma_load_2d(wbuf_ptr + lbuf_off[b], &map_resid, &lbar[b], n0 + c * 32, wrow0);
             }
           };
-          if (c_begin < ce) issue_resid(c_begin * 32);        // in flight while the MMAs of this unit still run
+          if (n_lbuf == 2 && lane == 0) bulk_wait_read0();    // the previous unit's fp32 stores have left the staging block
+          for (int c = c_begin; c < c_begin + n_lbuf; ++c) issue_resid(c);   // in flight while the MMAs of this unit still run
           mbar_wait(&tfull[acc], acc_phase);
           tc_fence_after();
 #pragma unroll 1
@@ -357,7 +362,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int n_ok = p.N - (n0 + c0);                 // >= 32 except for the last chunk of the row (16)
             uint32_t r[32];
             tmem_ld<32>(taddr + c0, r);
-            mbar_wait(lbar, lphase); lphase ^= 1;             // residual block has landed
+            const int lb = (c - c_begin) % n_lbuf;
+            mbar_wait(&lbar[lb], (lphase >> lb) & 1); lphase ^= 1u << lb;   // residual block has landed
+            const uint32_t lbuf = wbuf + lbuf_off[lb];
             float y[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -366,7 +373,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               y[4 * j] = rs.x + b4.x; y[4 * j + 1] = rs.y + b4.y; y[4 * j + 2] = rs.z + b4.z; y[4 * j + 3] = rs.w + b4.w;
             }
             __syncwarp();                                     // every lane is done reading lbuf
-            if (c + 1 < ce) issue_resid(c0 + 32);             // next block streams in during the math / stores below
+            issue_resid(c + n_lbuf);                          // refill this buffer: streams in during the math / stores below
             tmem_wait_ld();
             if (n_ok >= 32) {
 #pragma unroll
