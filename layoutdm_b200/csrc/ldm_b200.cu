@@ -115,6 +115,7 @@ struct LdmHandle {
   int num_sms = 148;
   int64_t launches = 0;
   int gemm_dbg = 0;           // env LDM_GEMM_DEBUG (bring-up probe, see GemmParams::dbg)
+  int debug_generic_posterior = 0;   // env LDM_GENERIC_POSTERIOR=1: always take the all-classes posterior / sampling kernel (tests)
   int debug_stop_after = 0;   // test tap: stop the denoiser after this many launches (0 = run everything)
   bool prof = false;          // per-kernel CUDA-event timing (ldm_profile_begin/end)
   struct ProfRec { int cat; cudaEvent_t a, b; };
@@ -397,7 +398,11 @@ int step_impl(LdmHandle* h, int B, const long long* ids_in, int t_model, int t_p
   const int warps = B * h->S, blocks = (warps * 32 + 255) / 256;
   {
     ProfScope ps(h, CAT_EPILOGUE, st);
-    posterior_sample_kernel<<<blocks, 256, 0, st>>>(p);
+    bool group_path = p.constrained && p.logprob_in == nullptr && p.logprob_out == nullptr && !(p.cond_flags & COND_REFINE) &&
+                      (p.mode == SAMP_DETERMINISTIC || p.mode == SAMP_RANDOM || p.mode == SAMP_GUMBEL) && !h->debug_generic_posterior;
+    for (int g = 0; g < p.n_attr; ++g) group_path = group_path && p.grp_n[g] <= 32;
+    if (group_path) posterior_sample_group_kernel<<<blocks, 256, 0, st>>>(p);
+    else posterior_sample_kernel<<<blocks, 256, 0, st>>>(p);
   }
   CK(cudaGetLastError());
   return LDM_OK;
@@ -433,6 +438,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   h->G = desc->q_type == 0 ? desc->n_attr : 1;
   h->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("LDM_GEMM_DEBUG")) h->gemm_dbg = atoi(e);
+  if (const char* e = getenv("LDM_GENERIC_POSTERIOR")) h->debug_generic_posterior = atoi(e);
 #define TRY(x) do { rc = (x); if (rc) { ldm_destroy(h); return rc; } } while (0)
 
   TRY(dev_upload(h, &h->cat_emb, w->cat_emb, static_cast<size_t>(C) * d));

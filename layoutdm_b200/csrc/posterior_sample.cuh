@@ -38,9 +38,8 @@ LDM_DEVINL float log_add_exp(float a, float b) {   // util.py:19-21
   return m + logf(expf(a - m) + expf(b - m));
 }
 
-__global__ void __launch_bounds__(256) posterior_sample_kernel(const StepParams p) {
-  const int token = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (token >= p.n_layouts * p.S) return;
+// One token, every class (lane l: classes 4l..4l+3 and 128+l): any q_type, any sampling mode, log-prob in / out.
+LDM_DEVINL void posterior_token_generic(const StepParams& p, const int token, const int lane) {
   const int b = token / p.S, s = token % p.S;
   const int C = p.C;
   int cls[5]; bool valid[5];
@@ -249,6 +248,158 @@ __global__ void __launch_bounds__(256) posterior_sample_kernel(const StepParams 
   for (int j = 0; j < 5; ++j) {
     if (valid[j] && (score[j] > best || (score[j] == best && cls[j] < best_c))) { best = score[j]; best_c = cls[j]; }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+    if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+  }
+  if (lane == 0) p.ids_out[token] = best_c;
+}
+
+__global__ void __launch_bounds__(256) posterior_sample_kernel(const StepParams p) {
+  const int token = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (token >= p.n_layouts * p.S) return;
+  posterior_token_generic(p, token, lane);
+}
+
+// Group-centric variant for the constrained (per-attribute) diffusion: outside the token's vocabulary group (plus PAD and
+// MASK) the posterior is the constant log(1e-30), so only the <= 34 classes of the group are evaluated (lane l: class
+// grp_start + l; lanes 0 / 1 additionally PAD / MASK); the float64 log-softmax still runs over all C-1 logits.
+// Preconditions (checked by the host): constrained, mode in {deterministic, random, gumbel}, no log-prob input / output, no
+// refinement table, every group <= 32 classes.  A token whose best in-group log-probability is not far enough above
+// log(1e-30) for the out-of-group classes to be unreachable takes posterior_token_generic instead (warp-uniform), so
+// the result is the generic kernel's in every case.
+__global__ void __launch_bounds__(256) posterior_sample_group_kernel(const StepParams p) {
+  const int token = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (token >= p.n_layouts * p.S) return;
+  const int b = token / p.S, s = token % p.S;
+  const int C = p.C;
+  const int x_t = static_cast<int>(p.ids_in[token]);
+
+  // ---- conditioning: a fixed token is copied (its log-probabilities are 0 / log(1e-30)) ----
+  long long cs = 0; bool fixed = false;
+  if (p.cond_flags) {
+    cs = p.cond_seq[token];
+    fixed = (p.cond_flags & COND_HAS_MASK) && p.cond_mask[token];
+  }
+
+  // ---- predict_start: float64 log-sum-exp over the C-1 non-MASK logits (lane l: classes 4l..4l+3, 128+l) ----
+  const float* lrow = p.logits + (static_cast<size_t>(b) * 128 + s) * p.ld_logits;
+  double lse;
+  {
+    float l[5];
+    const float4 v = __ldg(reinterpret_cast<const float4*>(lrow) + lane);
+    l[0] = v.x; l[1] = v.y; l[2] = v.z; l[3] = v.w;
+    l[4] = (128 + lane < C) ? __ldg(lrow + 128 + lane) : 0.0f;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { const int c = j < 4 ? 4 * lane + j : 128 + lane; if (c < C - 1) mx = fmaxf(mx, l[j]); }
+    mx = warp_max(mx);
+    double dsum = 0.0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { const int c = j < 4 ? 4 * lane + j : 128 + lane; if (c < C - 1) dsum += exp(static_cast<double>(l[j]) - static_cast<double>(mx)); }
+    dsum = warp_sum_d(dsum);
+    lse = static_cast<double>(mx) + log(dsum);
+  }
+
+  const int g = s % p.n_attr;
+  const int gst = p.grp_start[g], gn = p.grp_n[g];
+  const float* tab = p.sched + static_cast<size_t>(g) * 8 * (p.T + 1);
+  const int t = p.t_post, tm1 = (t - 1 + (p.T + 1)) % (p.T + 1);
+  const int TT = p.T + 1;
+  const float lat = tab[0 * TT + t], lbt = tab[1 * TT + t], lct = tab[2 * TT + t];
+  const float lcat = tab[3 * TT + t], lcbt = tab[4 * TT + t], lcct = tab[5 * TT + t];
+  const float lcat1 = tab[3 * TT + tm1], lcbt1 = tab[4 * TT + tm1], lcct1 = tab[5 * TT + tm1], l1mcct1 = tab[7 * TT + tm1];
+  const bool is_mask = (x_t == p.mask_id);
+
+  // slot 0: group class gst + lane ; slot 1: PAD (lane 0) / MASK (lane 1)
+  int cls[2]; bool on[2];
+  cls[0] = gst + lane; on[0] = lane < gn;
+  cls[1] = lane == 0 ? p.pad_id : p.mask_id; on[1] = lane < 2;
+  float q[2], one[2], lp[2];
+  float qmax = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    q[j] = -INFINITY; one[j] = 0.0f;
+    if (on[j]) {
+      const int c = cls[j];
+      if (c != p.mask_id) {
+        const float lx0 = fminf(fmaxf(static_cast<float>(static_cast<double>(__ldg(lrow + c)) - lse), -70.0f), 0.0f);
+        const float v = (c == x_t) ? 0.0f : kLogEps;
+        const float lq = is_mask ? lcct : log_add_exp(v + lcat, lcbt);
+        one[j] = is_mask ? lct : log_add_exp(v + lat, lbt);
+        q[j] = lx0 - lq;
+      } else {
+        q[j] = kLogEps;
+        one[j] = is_mask ? 0.0f : kLogEps;
+      }
+      qmax = fmaxf(qmax, q[j]);
+    }
+  }
+  qmax = warp_max(qmax);
+  float qs = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) if (on[j]) qs += expf(q[j] - qmax);
+  const float L = logf(warp_sum(qs)) + qmax;
+  float lmax = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    lp[j] = -INFINITY;
+    if (on[j]) {
+      const float qn = q[j] - L;
+      const float ev = (cls[j] != p.mask_id) ? log_add_exp(qn + lcat1, lcbt1) : log_add_exp(qn + l1mcct1, lcct1);
+      lp[j] = fminf(fmaxf((ev + one[j]) + L, -70.0f), 0.0f);
+      if (fixed) lp[j] = (cls[j] == cs) ? 0.0f : kLogEps;
+      if ((p.cond_flags & COND_PAD_DISABLE) && (s % p.n_attr != 0) && cs != p.pad_id && cls[j] == p.pad_id) lp[j] = kLogEps;
+      lmax = fmaxf(lmax, lp[j]);
+    }
+  }
+  lmax = warp_max(lmax);
+  // every class outside the group sits at log(1e-30): it must be out of reach of the draw (see the header comment)
+  const float margin = p.mode == SAMP_DETERMINISTIC ? 0.0f : 40.0f * p.temperature;
+  if (!(lmax - kLogEps > margin)) { posterior_token_generic(p, token, lane); return; }
+
+  float score[2];
+  if (p.mode == SAMP_DETERMINISTIC) {
+    score[0] = lp[0]; score[1] = lp[1];
+  } else {
+    float lg[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) lg[j] = on[j] ? lp[j] / p.temperature : -INFINITY;
+    const unsigned long long tok = (static_cast<unsigned long long>(p.b_global0) + b) * static_cast<unsigned long long>(p.S) + s;
+    const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
+    const uint32_t tok_lo = static_cast<uint32_t>(tok), tok_hi = static_cast<uint32_t>(tok >> 32);
+    const uint32_t w1 = p.step_ctr & 0xFFFFFFu;
+    auto noise_word = [&](int c, uint32_t stream) {            // class c: Philox block c / 4, word c % 4
+      const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(c) >> 2, w1 | (stream << 24), tok_lo, tok_hi), key);
+      return (c & 3) == 0 ? r.x : (c & 3) == 1 ? r.y : (c & 3) == 2 ? r.z : r.w;
+    };
+    if (p.mode == SAMP_GUMBEL) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (j == 1 && lane >= 2) continue;                     // warp-uniform per slot except the two PAD / MASK lanes
+        const float u = u01_from_bits(noise_word(cls[j], 1u));
+        if (on[j]) lg[j] += -logf(-logf(u + 1e-30f) + 1e-30f);
+      }
+    }
+    float m = warp_max(fmaxf(lg[0], lg[1]));
+    float ex[2], sm = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { ex[j] = on[j] ? expf(lg[j] - m) : 0.0f; sm += ex[j]; }
+    sm = warp_sum(sm);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      score[j] = -INFINITY;
+      if (j == 1 && lane >= 2) continue;
+      const float e = -logf(u01_from_bits(noise_word(cls[j], 0u)));
+      if (on[j]) score[j] = (ex[j] / sm) / e;
+    }
+  }
+  float best = -INFINITY; int best_c = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    if (on[j] && (score[j] > best || (score[j] == best && cls[j] < best_c))) { best = score[j]; best_c = cls[j]; }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);

@@ -65,6 +65,11 @@ def test_step_epilogue_is_id_exact_on_reference_logits(name):
         torch.cuda.synchronize()
         assert (lp.cpu() - fx.logp(i)).abs().max() < 1e-4
         assert torch.equal(out.cpu(), fx.x_out[i]), f"{name} step {i}: {(out.cpu() != fx.x_out[i]).sum().item()} ids differ"
+        # without the log-prob output the constrained / random|gumbel|deterministic configurations take the group-centric
+        # kernel (posterior_sample_group_kernel): same ids
+        out2, _, _ = eng.step(fx.x_in[i].cuda(), t_model, t_post, fx.cfg_dict, cond, seed=fx.meta["noise_seed"], step_ctr=i,
+                              logits_in=fx.logits(i).cuda())
+        assert torch.equal(out2.cpu(), fx.x_out[i]), f"{name} step {i} (group kernel): {(out2.cpu() != fx.x_out[i]).sum().item()} ids differ"
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -87,6 +92,9 @@ def test_epilogue_every_step_against_oracle(name):
                               want_logprob=True, logits_in=logits.cuda())
         assert (lp.cpu() - lp_o).abs().max() < 1e-4
         bad += int((out.cpu() != want).sum())
+        out2, _, _ = eng.step(fx.x_in[i].cuda(), t_model, t_post, fx.cfg_dict, cond, seed=fx.meta["noise_seed"], step_ctr=i,
+                              logits_in=logits.cuda())            # group-centric kernel where eligible
+        bad += int((out2.cpu() != want).sum())
     assert bad == 0
 
 
