@@ -411,6 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           unsigned long long w0, w1;
           uint32_t spins = 0;
           do {
+            if (spins) __nanosleep(64);                        // the partner is a few hundred ns behind at most: poll gently
             w0 = ld_ll_word(peer_w); w1 = ld_ll_word(peer_w + 1);
             if (++spins > (1u << 24)) { printf("LN statistics exchange timed out (unit %d)\n", o); __trap(); }
           } while (static_cast<unsigned>(w0 >> 32) != p.ln_epoch || static_cast<unsigned>(w1 >> 32) != p.ln_epoch);
