@@ -63,7 +63,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
   uint64_t* o_staged = bars + 6;  // 256 arrivals: O staging tile written
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // shuffle: provably warp-uniform (uniform-register control warps)
   const int n_items = n_layouts * n_heads;                     // item = layout * n_heads + head
   const int step = gridDim.x;
 
@@ -82,8 +82,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
 
   if (warp == 0) {
-    // ===================== producer: loads two items ahead, stores O =====================
-    if (lane == 0) {
+    // ===================== producer: loads two items ahead, stores O (whole warp loops, one elected lane issues) =====================
+    {
       auto load = [&](int item, int b) {
         const int h = item % n_heads, row0 = (item / n_heads) * 128;
         uint8_t* buf = smem + b * kAttBuf;
@@ -93,25 +93,31 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
         tma_load_2d(buf + kAttOffV, &map_qkv, &qkv_full[b], 2 * n_heads * 64 + h * 64, row0);
       };
       const int first = blockIdx.x;
-      if (first < n_items) load(first, 0);
-      if (first + step < n_items) load(first + step, 1);
+      if (elect_one()) {
+        if (first < n_items) load(first, 0);
+        if (first + step < n_items) load(first + step, 1);
+      }
+      __syncwarp();
       int hi = 0;
       for (int item = first; item < n_items; item += step, ++hi) {
         const int b = hi & 1;
         const int h = item % n_heads, row0 = (item / n_heads) * 128;
         mbar_wait(o_staged, hi & 1);
-        tma_store_2d(&map_att, smem_u32(smem + b * kAttBuf + kAttOffO), h * 64, row0);
-        bulk_commit();
-        if (item + 2 * step < n_items) {
-          bulk_wait_read0();                                     // the store has read the staging tile: the buffer is free
-          load(item + 2 * step, b);
+        if (elect_one()) {
+          tma_store_2d(&map_att, smem_u32(smem + b * kAttBuf + kAttOffO), h * 64, row0);
+          bulk_commit();
+          if (item + 2 * step < n_items) {
+            bulk_wait_read0();                                   // the store has read the staging tile: the buffer is free
+            load(item + 2 * step, b);
+          }
         }
+        __syncwarp();
       }
       bulk_wait_all();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc_s = make_idesc_f16(128, 128, BF16 ? 1 : 0);                 // A, B K-major
       constexpr uint32_t idesc_o = make_idesc_f16(128, 64, BF16 ? 1 : 0) | (1u << 16);     // B (= V) MN-major
       int hi = 0;
@@ -122,23 +128,25 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
         // ---- S = Q K^T (S of the previous item was consumed before its p_ready) ----
         mbar_wait(&qkv_full[b], (hi >> 1) & 1);
         tc_fence_after();
-        {
+        if (elect_one()) {
           const uint64_t da = make_smem_desc_sw128(sbuf + kAttOffQ), db = make_smem_desc_sw128(sbuf + kAttOffK);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16(tS, da + 2 * k, db + 2 * k, idesc_s, k != 0);
+          umma_commit(s_full);
         }
-        umma_commit(s_full);
+        __syncwarp();
         // ---- O = P V ----
         mbar_wait(p_ready, ph);                                  // P written (and S fully read)
         if (hi > 0) mbar_wait(o_done, (hi - 1) & 1);             // previous O has been read out of TMEM
         tc_fence_after();
-        {
+        if (elect_one()) {
           const uint64_t da = make_smem_desc_sw128(sbuf + kAttOffP), db = make_smem_desc_mn_sw128(sbuf + kAttOffV);
 #pragma unroll
           for (int k = 0; k < 8; ++k)                            // 16 keys per MMA: P advances 32 B inside a k-block / 16 KB
             umma_f16(tO, da + (k >> 2) * (kAttTile >> 4) + 2 * (k & 3), db + k * (2048 >> 4), idesc_o, k != 0);   // V: 16 rows
+          umma_commit(o_full);
         }
-        umma_commit(o_full);
+        __syncwarp();
       }
     }
   } else {

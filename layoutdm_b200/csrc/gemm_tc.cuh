@@ -114,7 +114,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   float* sbias = reinterpret_cast<float*>(smem + SM::kOffBias);
   static_assert((2 * STAGES + 20) * 8 + 4 <= SM::kBarBytes, "barrier block overflow");
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the producer / MMA loops (addresses,
+  // descriptors, barrier phases) in uniform registers -- with a per-lane index every tcgen05.mma paid ~25 instructions of
+  // R2UR.BROADCAST / ELECT glue and the tensor pipe idled half the time (profiles r01q)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int num_kb = (p.K + kBK - 1) / kBK;
   const uint32_t cta_rank = cluster_ctarank();               // 0 = leader
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
@@ -146,8 +149,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer (one thread in each CTA) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    {
       int stage = 0; uint32_t phase = 0;
       for (int o = pair; o < n_outer; o += n_pairs)
       for (int i = 0; i < n_inner; ++i) {
@@ -159,19 +162,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * SM::kStageBytes;
           const uint32_t lead_full = mapa_shared(smem_u32(&full[stage]), 0);
-          if (p.dbg & 2) { mbar_arrive_cluster(lead_full); }
-          else {
-          mbar_arrive_expect_tx_cluster(lead_full, SM::kStageBytes);
-          tma_load_2d_2cta(sa, &map_a, lead_full, kb * kBK, m_blk * kBM);
-          tma_load_2d_2cta(sa + kATileBytes, &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * b_half);
+          if (elect_one()) {
+            if (p.dbg & 2) { mbar_arrive_cluster(lead_full); }
+            else {
+              mbar_arrive_expect_tx_cluster(lead_full, SM::kStageBytes);
+              tma_load_2d_2cta(sa, &map_a, lead_full, kb * kBK, m_blk * kBM);
+              tma_load_2d_2cta(sa + kATileBytes, &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * b_half);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread of the leader CTA) =====================
-    if (lane == 0 && cta_rank == 0) {
+    // ===================== MMA issuer (warp 1 of the leader CTA loops, one elected lane issues) =====================
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = make_idesc_f16(2 * kBM, UMMA_N, BF16 ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -190,13 +196,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint64_t da = make_smem_desc_sw128(sa);
           const uint64_t db = make_smem_desc_sw128(sa + kATileBytes);
           const int nk = min(kBK, p.K - kb * kBK) / kUmmaK;     // K tail: TMA zero-fills, skip the zero k-steps
-          if (!(p.dbg & 1))
-          for (int k = 0; k < nk; ++k)
-            umma_f16_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc_t, (kb | k) != 0);   // +32 B per k-step (>>4 = 2)
-          umma_commit_2cta_mc(&empty[stage], static_cast<uint16_t>(0b11));       // free the stage in both CTAs
+          if (elect_one()) {
+            if (!(p.dbg & 1)) {
+              if (nk == kBK / kUmmaK) {
+#pragma unroll
+                for (int k = 0; k < kBK / kUmmaK; ++k)
+                  umma_f16_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc_t, (kb | k) != 0);   // +32 B per k-step (>>4 = 2)
+              } else {
+                for (int k = 0; k < nk; ++k) umma_f16_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc_t, (kb | k) != 0);
+              }
+            }
+            umma_commit_2cta_mc(&empty[stage], static_cast<uint16_t>(0b11));       // free the stage in both CTAs
+            if (kb == num_kb - 1) umma_commit_2cta_mc(&tfull[acc], static_cast<uint16_t>(0b11));   // accumulator ready in both CTAs
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2cta_mc(&tfull[acc], static_cast<uint16_t>(0b11));           // accumulator ready in both CTAs
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
