@@ -59,19 +59,25 @@ struct GemmParams {
   int dbg;                // bring-up probe (env LDM_GEMM_DEBUG), bit mask: 1 = skip the MMAs, 2 = skip the TMA operand loads, 4 = skip the epilogue body; results are garbage
 };
 
-template <int UMMA_N, int STAGES, int EPI>
+constexpr int kAResSlots = 8;   // A-resident mode: K <= 512, the row block's whole A operand (8 k-blocks) stays in smem
+
+// ARES: the 128 x K activation block of the CTA is loaded ONCE per row block and reused by all N tiles; only the weight
+// half-tiles stream through the ring (the K=464 GEMMs are bound by the bytes each SM pulls out of L2: -42 %).
+template <int UMMA_N, int STAGES, int EPI, bool ARES = false>
 struct GemmSmem {
   static constexpr int kBHalfBytes = (UMMA_N / 2) * kBK * 2;     // each CTA of the pair holds half of the weight tile
-  static constexpr int kStageBytes = kATileBytes + kBHalfBytes;
+  static constexpr int kStageBytes = ARES ? kBHalfBytes : kATileBytes + kBHalfBytes;
+  static constexpr int kAResBytes = ARES ? kAResSlots * kATileBytes : 0;
   static_assert(kBHalfBytes % 1024 == 0, "half weight tile must keep 1024-B (swizzle atom) alignment");
   // per-epilogue-warp staging: [0,4K) 32x32 fp32 store block (128B swizzle) / 16-bit store block (64B swizzle);
   // LN: [4K,6K) 16-bit store block, [6K,10K) residual load block (128B swizzle)
-  static constexpr int kWarpStage = EPI == EPI_LN ? 10240 : 4096;
+  static constexpr int kWarpStage = EPI == EPI_LN ? 10240 : (ARES ? 2048 : 4096);
   static constexpr int kStagingBytes = 8 * kWarpStage;
-  static constexpr int kBarBytes = 256;
+  static constexpr int kBarBytes = 512;
   static constexpr int kBiasBytes = 1856 * 4;   // bias (and, for LN, gamma / beta) vectors of the layer
   static constexpr int kStatBytes = 4 * kBM * 8;  // LN: per-row (sum, sumsq) partials of the two column halves, per accumulator
-  static constexpr int kOffStaging = STAGES * kStageBytes;
+  static constexpr int kOffRing = kAResBytes;                      // [A-resident slots][ring stages]...
+  static constexpr int kOffStaging = kOffRing + STAGES * kStageBytes;
   static constexpr int kOffBars = kOffStaging + kStagingBytes;
   static constexpr int kOffBias = kOffBars + kBarBytes;
   static constexpr int kOffStat = kOffBias + kBiasBytes;
@@ -83,7 +89,7 @@ struct GemmSmem {
 // tcgen05.mma issued by the leader CTA (rank 0): A = 128 rows from each CTA's own smem, B = UMMA_N/2 weight rows from each
 // CTA's smem, D = 128 accumulator rows in each CTA's TMEM.  A pair walks all N tiles of its 256-row block back to back
 // (A tiles stay L2-hot, and the LN epilogue sees complete rows).
-template <int BN_STORE, int UMMA_N, int STAGES, int EPI, bool BF16>
+template <int BN_STORE, int UMMA_N, int STAGES, int EPI, bool BF16, bool ARES = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out,     // main output: 32x32 blocks (16-bit: 64B swizzle, fp32: 128B swizzle)
@@ -91,8 +97,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ CUtensorMap map_yout,    // LN: fp32 pre-norm sum (store) when p.y_out
                const __grid_constant__ CUtensorMap map_out32,   // LN: fp32 normalised output (store) when p.out32
                const GemmParams p) {
-  using SM = GemmSmem<UMMA_N, STAGES, EPI>;
+  using SM = GemmSmem<UMMA_N, STAGES, EPI, ARES>;
   using O = OpT<BF16>;
+  static_assert(!ARES || EPI == EPI_QKV || EPI == EPI_RELU, "A-resident mode: 16-bit plain epilogues only");
   static_assert(UMMA_N % 16 == 0 && UMMA_N <= 256 && BN_STORE <= UMMA_N, "invalid UMMA shape");
   constexpr int kAccStride = 256;            // TMEM columns between the two accumulators
   constexpr uint32_t kTmemCols = 512;
@@ -110,9 +117,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tfull = bars + 2 * STAGES;       // per CTA: accumulator ready (multicast commit)
   uint64_t* tempty = bars + 2 * STAGES + 2;  // leader's copy: 16 warp arrivals (8 epilogue warps x 2 CTAs)
   uint64_t* lbars = bars + 2 * STAGES + 4;   // LN: two residual-load barriers per epilogue warp
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 20);
+  uint64_t* afull = bars + 2 * STAGES + 20;  // ARES: leader's copy live (A k-block of this row block landed in both CTAs)
+  uint64_t* aempty = afull + kAResSlots;     // ARES: per CTA, the last N tile's MMAs are done with the A k-block
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 20 + 2 * kAResSlots);
   float* sbias = reinterpret_cast<float*>(smem + SM::kOffBias);
-  static_assert((2 * STAGES + 20) * 8 + 4 <= SM::kBarBytes, "barrier block overflow");
+  static_assert((2 * STAGES + 20 + 2 * kAResSlots) * 8 + 4 <= SM::kBarBytes, "barrier block overflow");
 
   // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the producer / MMA loops (addresses,
   // descriptors, barrier phases) in uniform registers -- with a per-lane index every tcgen05.mma paid ~25 instructions of
@@ -139,6 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }
     for (int i = 0; i < 16; ++i) mbar_init(&lbars[i], 1);
+    for (int i = 0; i < kAResSlots; ++i) { mbar_init(&afull[i], 2); mbar_init(&aempty[i], 1); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2cta(tmem_ptr, kTmemCols);
@@ -151,37 +161,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
     {
-      int stage = 0; uint32_t phase = 0;
-      for (int o = pair; o < n_outer; o += n_pairs)
+      int stage = 0; uint32_t phase = 0, a_phase = 0;
+      for (int o = pair; o < n_outer; o += n_pairs) {
       for (int i = 0; i < n_inner; ++i) {
         const int sup = p.tile_sched ? o / p.n_tiles : o, n_blk = p.tile_sched ? o % p.n_tiles : i;
         const int m_blk = 2 * sup + static_cast<int>(cta_rank);
         // weight rows per CTA (the TMA box stays UMMA_N / 2 rows: rows past b_half are unused)
         const int b_half = (EPI == EPI_LN ? (n_blk == 0 ? BN_STORE : UMMA_N) : min(UMMA_N, p.N - n_blk * BN_STORE)) / 2;
         for (int kb = 0; kb < num_kb; ++kb) {
+          if constexpr (ARES) {
+            if (i == 0) {                                      // this row block's A k-block: loaded once, reused by every N tile
+              mbar_wait(&aempty[kb], a_phase ^ 1);
+              const uint32_t lead_afull = mapa_shared(smem_u32(&afull[kb]), 0);
+              if (elect_one()) {
+                if (p.dbg & 2) { mbar_arrive_cluster(lead_afull); }
+                else {
+                  mbar_arrive_expect_tx_cluster(lead_afull, kATileBytes);
+                  tma_load_2d_2cta(smem + kb * kATileBytes, &map_a, lead_afull, kb * kBK, m_blk * kBM);
+                }
+              }
+              __syncwarp();
+            }
+          }
           mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * SM::kStageBytes;
+          uint8_t* sa = smem + SM::kOffRing + stage * SM::kStageBytes;
           const uint32_t lead_full = mapa_shared(smem_u32(&full[stage]), 0);
           if (elect_one()) {
             if (p.dbg & 2) { mbar_arrive_cluster(lead_full); }
             else {
               mbar_arrive_expect_tx_cluster(lead_full, SM::kStageBytes);
-              tma_load_2d_2cta(sa, &map_a, lead_full, kb * kBK, m_blk * kBM);
-              tma_load_2d_2cta(sa + kATileBytes, &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * b_half);
+              if constexpr (!ARES) tma_load_2d_2cta(sa, &map_a, lead_full, kb * kBK, m_blk * kBM);
+              tma_load_2d_2cta(sa + (ARES ? 0 : kATileBytes), &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * b_half);
             }
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      a_phase ^= 1;
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp 1 of the leader CTA loops, one elected lane issues) =====================
     if (cta_rank == 0) {
       constexpr uint32_t idesc = make_idesc_f16(2 * kBM, UMMA_N, BF16 ? 1 : 0);
-      int stage = 0; uint32_t phase = 0;
+      int stage = 0; uint32_t phase = 0, a_phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int o = pair; o < n_outer; o += n_pairs)
+      for (int o = pair; o < n_outer; o += n_pairs) {
       for (int i = 0; i < n_inner; ++i) {
         const int n_blk_mma = p.tile_sched ? o % p.n_tiles : i;
         const int nw = EPI == EPI_LN ? (n_blk_mma == 0 ? BN_STORE : UMMA_N) : min(UMMA_N, p.N - n_blk_mma * BN_STORE);   // last tile may be narrower
@@ -190,11 +216,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);                    // both CTAs' A and B halves have landed
+          if constexpr (ARES) { if (i == 0) mbar_wait(&afull[kb], a_phase); }   // this row block's A k-block is in place
+          mbar_wait(&full[stage], phase);                    // both CTAs' operand tiles have landed
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * SM::kStageBytes);
-          const uint64_t da = make_smem_desc_sw128(sa);
-          const uint64_t db = make_smem_desc_sw128(sa + kATileBytes);
+          const uint32_t sr = smem_u32(smem + SM::kOffRing + stage * SM::kStageBytes);
+          const uint64_t da = make_smem_desc_sw128(ARES ? smem_u32(smem + kb * kATileBytes) : sr);
+          const uint64_t db = make_smem_desc_sw128(ARES ? sr : sr + kATileBytes);
           const int nk = min(kBK, p.K - kb * kBK) / kUmmaK;     // K tail: TMA zero-fills, skip the zero k-steps
           if (elect_one()) {
             if (!(p.dbg & 1)) {
@@ -207,12 +234,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
             umma_commit_2cta_mc(&empty[stage], static_cast<uint16_t>(0b11));       // free the stage in both CTAs
+            if constexpr (ARES) { if (i == n_inner - 1) umma_commit_2cta_mc(&aempty[kb], static_cast<uint16_t>(0b11)); }
             if (kb == num_kb - 1) umma_commit_2cta_mc(&tfull[acc], static_cast<uint16_t>(0b11));   // accumulator ready in both CTAs
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      a_phase ^= 1;
       }
     }
   } else {

@@ -292,7 +292,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       GemmParams p{M, kQkvN, d, kQkvN / 256, h->bqkv[l], h->qkv16, kQkvN, 1.0f / sqrtf(static_cast<float>(d / h->desc.n_heads)), 8 * kHeadPad};
       p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles);
       ProfScope ps(h, CAT_QKV, st);
-      gemm_tc_kernel<256, 256, 5, EPI_QKV, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 5, EPI_QKV>::kBytes, st>>>(
+      gemm_tc_kernel<256, 256, 4, EPI_QKV, BF16, true><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 4, EPI_QKV, true>::kBytes, st>>>(
           h->m_x16, h->m_wqkv[l], h->b_qkv16, h->b_qkv16, h->b_qkv16, h->b_qkv16, p);
     }
     LDM_STAGE_DONE();
@@ -314,7 +314,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       GemmParams p{M, ff, d, (ff + 255) / 256, h->b1[l], h->hid16, ff, 1.0f, 0};   // 7 tiles of 256 columns + one of 64
       p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles);
       ProfScope ps(h, CAT_FF1, st);
-      gemm_tc_kernel<256, 256, 5, EPI_RELU, BF16><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 5, EPI_RELU>::kBytes, st>>>(
+      gemm_tc_kernel<256, 256, 4, EPI_RELU, BF16, true><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 4, EPI_RELU, true>::kBytes, st>>>(
           h->m_z16, h->m_w1[l], h->b_hid16, h->b_hid16, h->b_hid16, h->b_hid16, p);
     }
     LDM_STAGE_DONE();
@@ -517,14 +517,14 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   if (cudaDeviceSynchronize() != cudaSuccess) { ldm_destroy(h); return fail(LDM_ERR_CUDA, "weight packing failed: %s", cudaGetErrorString(cudaGetLastError())); }
 
   if (h->bf16) {
-    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, true>, GemmSmem<256, 5, EPI_QKV>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_RELU, true>, GemmSmem<256, 5, EPI_RELU>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, 4, EPI_QKV, true, true>, GemmSmem<256, 4, EPI_QKV, true>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, 4, EPI_RELU, true, true>, GemmSmem<256, 4, EPI_RELU, true>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, true>, GemmSmem<160, 5, EPI_F32>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<224, 240, 4, EPI_LN, true>, GemmSmem<240, 4, EPI_LN>::kBytes)));
     TRY((set_smem(attention_kernel<true>, kAttSmemBytes)));
   } else {
-    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, false>, GemmSmem<256, 5, EPI_QKV>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_RELU, false>, GemmSmem<256, 5, EPI_RELU>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, 4, EPI_QKV, false, true>, GemmSmem<256, 4, EPI_QKV, true>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, 4, EPI_RELU, false, true>, GemmSmem<256, 4, EPI_RELU, true>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, false>, GemmSmem<160, 5, EPI_F32>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<224, 240, 4, EPI_LN, false>, GemmSmem<240, 4, EPI_LN>::kBytes)));
     TRY((set_smem(attention_kernel<false>, kAttSmemBytes)));
