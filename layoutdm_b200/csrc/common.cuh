@@ -192,6 +192,18 @@ LDM_DEVINL uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// K-major operand tile whose rows hold only 16 elements (32 B) with the 32-byte swizzle (TMA SWIZZLE_32B):
+// 8-row groups are 256 B apart (SBO), layout type 6 = SWIZZLE_32B.  Used for the K tail of the A-resident block.
+LDM_DEVINL uint64_t make_smem_desc_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16: D=f32, A/B = f16 (0) or bf16 (1), both K-major, M x N.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int ab_format) {
   return (1u << 4) | (static_cast<uint32_t>(ab_format) << 7) | (static_cast<uint32_t>(ab_format) << 10) |

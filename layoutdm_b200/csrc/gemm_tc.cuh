@@ -67,7 +67,9 @@ template <int UMMA_N, int STAGES, int EPI, bool ARES = false>
 struct GemmSmem {
   static constexpr int kBHalfBytes = (UMMA_N / 2) * kBK * 2;     // each CTA of the pair holds half of the weight tile
   static constexpr int kStageBytes = ARES ? kBHalfBytes : kATileBytes + kBHalfBytes;
-  static constexpr int kAResBytes = ARES ? kAResSlots * kATileBytes : 0;
+  // the K = 464 block = 7 full k-blocks + a 16-column tail, kept as a 128 x 32 B tile (32-byte swizzle, its own tensor map)
+  static constexpr int kATailBytes = kBM * kUmmaK * 2;
+  static constexpr int kAResBytes = ARES ? (kAResSlots - 1) * kATileBytes + kATailBytes : 0;
   static_assert(kBHalfBytes % 1024 == 0, "half weight tile must keep 1024-B (swizzle atom) alignment");
   // per-epilogue-warp staging: [0,4K) 32x32 fp32 store block (128B swizzle) / 16-bit store block (64B swizzle);
   // LN: [4K,6K) 16-bit store block, [6K,10K) residual load block (128B swizzle)
@@ -75,7 +77,7 @@ struct GemmSmem {
   static constexpr int kStagingBytes = 8 * kWarpStage;
   static constexpr int kBarBytes = 512;
   static constexpr int kBiasBytes = 1856 * 4;   // bias (and, for LN, gamma / beta) vectors of the layer
-  static constexpr int kStatBytes = 4 * kBM * 8;  // LN: per-row (sum, sumsq) partials of the two column halves, per accumulator
+  static constexpr int kStatBytes = EPI == EPI_LN ? 4 * kBM * 8 : 0;  // LN: per-row (sum, sumsq) partials of the two column halves, per accumulator
   static constexpr int kOffRing = kAResBytes;                      // [A-resident slots][ring stages]...
   static constexpr int kOffStaging = kOffRing + STAGES * kStageBytes;
   static constexpr int kOffBars = kOffStaging + kStagingBytes;
@@ -95,7 +97,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ CUtensorMap map_out,     // main output: 32x32 blocks (16-bit: 64B swizzle, fp32: 128B swizzle)
                const __grid_constant__ CUtensorMap map_resid,   // LN: fp32 residual (load)
                const __grid_constant__ CUtensorMap map_yout,    // LN: fp32 pre-norm sum (store) when p.y_out
-               const __grid_constant__ CUtensorMap map_out32,   // LN: fp32 normalised output (store) when p.out32
+               const __grid_constant__ CUtensorMap map_out32,   // LN: fp32 normalised output (store) when p.out32; ARES: the A operand's K tail (16 x 128 box, 32B swizzle)
                const GemmParams p) {
   using SM = GemmSmem<UMMA_N, STAGES, EPI, ARES>;
   using O = OpT<BF16>;
@@ -176,8 +178,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               if (elect_one()) {
                 if (p.dbg & 2) { mbar_arrive_cluster(lead_afull); }
                 else {
-                  mbar_arrive_expect_tx_cluster(lead_afull, kATileBytes);
-                  tma_load_2d_2cta(smem + kb * kATileBytes, &map_a, lead_afull, kb * kBK, m_blk * kBM);
+                  const bool tail = (kb == num_kb - 1) && (p.K & (kBK - 1)) != 0;   // K % 64 == 16 (checked by the host)
+                  mbar_arrive_expect_tx_cluster(lead_afull, tail ? SM::kATailBytes : kATileBytes);
+                  tma_load_2d_2cta(smem + kb * kATileBytes, tail ? &map_out32 : &map_a, lead_afull, kb * kBK, m_blk * kBM);
                 }
               }
               __syncwarp();
@@ -220,7 +223,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&full[stage], phase);                    // both CTAs' operand tiles have landed
           tc_fence_after();
           const uint32_t sr = smem_u32(smem + SM::kOffRing + stage * SM::kStageBytes);
-          const uint64_t da = make_smem_desc_sw128(ARES ? smem_u32(smem + kb * kATileBytes) : sr);
+          const bool a_tail = ARES && (kb == num_kb - 1) && (p.K & (kBK - 1)) != 0;
+          const uint64_t da = a_tail ? make_smem_desc_sw32(smem_u32(smem + kb * kATileBytes))
+                                     : make_smem_desc_sw128(ARES ? smem_u32(smem + kb * kATileBytes) : sr);
           const uint64_t db = make_smem_desc_sw128(ARES ? sr : sr + kATileBytes);
           const int nk = min(kBK, p.K - kb * kBK) / kUmmaK;     // K tail: TMA zero-fills, skip the zero k-steps
           if (elect_one()) {

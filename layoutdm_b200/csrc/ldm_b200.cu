@@ -87,6 +87,20 @@ int make_block_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t col
   return LDM_OK;
 }
 
+// K tail of an activation operand for the A-resident GEMMs: 16 columns x 128 rows starting at any column, 32-byte swizzle
+int make_tail_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, bool bf16) {
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kUmmaK), static_cast<cuuint32_t>(kBM)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LDM_ERR_CUDA, "cuTensorMapEncodeTiled (tail map) failed (%d) rows=%llu cols=%llu", (int)r,
+                                     (unsigned long long)rows, (unsigned long long)cols);
+  return LDM_OK;
+}
+
 // (B,S,C) contiguous <-> padded internal logits [B*128][160]
 __global__ void logits_scatter_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_layouts, int S, int C) {
   const size_t n = static_cast<size_t>(n_layouts) * S * C;
@@ -135,6 +149,7 @@ struct LdmHandle {
   long long* ids_final = nullptr;
   long long *c_seq = nullptr, *c_seq_orig = nullptr; unsigned char* c_mask = nullptr; float* c_tbl = nullptr;  // staging for ldm_sample_host
   CUtensorMap m_x16, m_att16, m_z16, m_hid16, m_qkv16;                       // A operands (128 x 64 boxes)
+  CUtensorMap t_x16, t_z16;                                                  // K tails of the A-resident operands (128 x 16 boxes)
   CUtensorMap b_qkv16, b_hid16, b_z16, b_x16, b_x32, b_y32, b_logits;  // epilogue 32 x 32 blocks
   std::vector<void*> owned;
 };
@@ -255,6 +270,8 @@ int ensure_workspace(LdmHandle* h, int n_layouts) {
   if ((rc = make_map(&h->m_qkv16, h->qkv16, M, kQkvN, kBM, h->bf16))) return rc;  // attention's Q / K / V head tiles
   if ((rc = make_map(&h->m_z16, h->z16, M, d, kBM, h->bf16))) return rc;
   if ((rc = make_map(&h->m_hid16, h->hid16, M, ff, kBM, h->bf16))) return rc;
+  if ((rc = make_tail_map(&h->t_x16, h->x16, M, d, h->bf16))) return rc;
+  if ((rc = make_tail_map(&h->t_z16, h->z16, M, d, h->bf16))) return rc;
   if ((rc = make_block_map(&h->b_qkv16, h->qkv16, M, kQkvN, 2, h->bf16))) return rc;
   if ((rc = make_block_map(&h->b_hid16, h->hid16, M, ff, 2, h->bf16))) return rc;
   if ((rc = make_block_map(&h->b_z16, h->z16, M, d, 2, h->bf16))) return rc;
@@ -292,8 +309,8 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       GemmParams p{M, kQkvN, d, kQkvN / 256, h->bqkv[l], h->qkv16, kQkvN, 1.0f / sqrtf(static_cast<float>(d / h->desc.n_heads)), 8 * kHeadPad};
       p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles);
       ProfScope ps(h, CAT_QKV, st);
-      gemm_tc_kernel<256, 256, 4, EPI_QKV, BF16, true><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 4, EPI_QKV, true>::kBytes, st>>>(
-          h->m_x16, h->m_wqkv[l], h->b_qkv16, h->b_qkv16, h->b_qkv16, h->b_qkv16, p);
+      gemm_tc_kernel<256, 256, 5, EPI_QKV, BF16, true><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 5, EPI_QKV, true>::kBytes, st>>>(
+          h->m_x16, h->m_wqkv[l], h->b_qkv16, h->b_qkv16, h->b_qkv16, h->t_x16, p);
     }
     LDM_STAGE_DONE();
     {
@@ -314,8 +331,8 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       GemmParams p{M, ff, d, (ff + 255) / 256, h->b1[l], h->hid16, ff, 1.0f, 0};   // 7 tiles of 256 columns + one of 64
       p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles);
       ProfScope ps(h, CAT_FF1, st);
-      gemm_tc_kernel<256, 256, 4, EPI_RELU, BF16, true><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 4, EPI_RELU, true>::kBytes, st>>>(
-          h->m_z16, h->m_w1[l], h->b_hid16, h->b_hid16, h->b_hid16, h->b_hid16, p);
+      gemm_tc_kernel<256, 256, 5, EPI_RELU, BF16, true><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 5, EPI_RELU, true>::kBytes, st>>>(
+          h->m_z16, h->m_w1[l], h->b_hid16, h->b_hid16, h->b_hid16, h->t_z16, p);
     }
     LDM_STAGE_DONE();
     {  // FF2 + bias + residual ; next block's AdaLN(h, t) (fp32 residual + 16-bit operand) or the head LayerNorm   [fused epilogue]
@@ -517,14 +534,14 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   if (cudaDeviceSynchronize() != cudaSuccess) { ldm_destroy(h); return fail(LDM_ERR_CUDA, "weight packing failed: %s", cudaGetErrorString(cudaGetLastError())); }
 
   if (h->bf16) {
-    TRY((set_smem(gemm_tc_kernel<256, 256, 4, EPI_QKV, true, true>, GemmSmem<256, 4, EPI_QKV, true>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<256, 256, 4, EPI_RELU, true, true>, GemmSmem<256, 4, EPI_RELU, true>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, true, true>, GemmSmem<256, 5, EPI_QKV, true>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_RELU, true, true>, GemmSmem<256, 5, EPI_RELU, true>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, true>, GemmSmem<160, 5, EPI_F32>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<224, 240, 4, EPI_LN, true>, GemmSmem<240, 4, EPI_LN>::kBytes)));
     TRY((set_smem(attention_kernel<true>, kAttSmemBytes)));
   } else {
-    TRY((set_smem(gemm_tc_kernel<256, 256, 4, EPI_QKV, false, true>, GemmSmem<256, 4, EPI_QKV, true>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<256, 256, 4, EPI_RELU, false, true>, GemmSmem<256, 4, EPI_RELU, true>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, false, true>, GemmSmem<256, 5, EPI_QKV, true>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_RELU, false, true>, GemmSmem<256, 5, EPI_RELU, true>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, false>, GemmSmem<160, 5, EPI_F32>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<224, 240, 4, EPI_LN, false>, GemmSmem<240, 4, EPI_LN>::kBytes)));
     TRY((set_smem(attention_kernel<false>, kAttSmemBytes)));
