@@ -135,7 +135,7 @@ struct LdmHandle {
   struct ProfRec { int cat; cudaEvent_t a, b; };
   std::vector<ProfRec> prof_recs;
   // parameters (device)
-  float *cat_emb = nullptr, *pos = nullptr, *adaln = nullptr, *sched = nullptr;
+  float *cat_emb = nullptr, *pos = nullptr, *adaln = nullptr, *sched = nullptr, *lae = nullptr;
   void *wqkv[kMaxLayers] = {}, *wo[kMaxLayers] = {}, *w1[kMaxLayers] = {}, *w2[kMaxLayers] = {}, *whead = nullptr;
   float *bqkv[kMaxLayers] = {}, *bo[kMaxLayers] = {}, *b1[kMaxLayers] = {}, *b2[kMaxLayers] = {}, *ln2w[kMaxLayers] = {}, *ln2b[kMaxLayers] = {};
   float *hlnw = nullptr, *hlnb = nullptr;
@@ -401,7 +401,7 @@ int step_impl(LdmHandle* h, int B, const long long* ids_in, int t_model, int t_p
     p.grp_start[g] = g == 0 ? 0 : h->desc.n_cat + (g - 1) * h->desc.n_bins;
     p.grp_n[g] = g == 0 ? h->desc.n_cat : h->desc.n_bins;
   }
-  p.T = h->T; p.t_post = t_post; p.sched = h->sched;
+  p.T = h->T; p.t_post = t_post; p.sched = h->sched; p.lae = h->lae;
   p.logits = h->logits; p.ld_logits = kLogitLd; p.logprob_in = logprob_in; p.ids_in = ids_in;
   if (cond && cond->seq) {
     p.cond_seq = reinterpret_cast<const long long*>(cond->seq); p.cond_mask = cond->mask;
@@ -530,6 +530,9 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
       build_schedule(*desc, N, sch.data() + static_cast<size_t>(g) * 8 * (T + 1));
     }
     TRY(dev_upload(h, &h->sched, sch.data(), sch.size()));
+    TRY(dev_alloc(h, &h->lae, static_cast<size_t>(h->G) * (T + 1) * 4));
+    lae_table_kernel<<<(h->G * (T + 1) + 127) / 128, 128>>>(h->sched, h->lae, h->G, T + 1);
+    if (cudaGetLastError() != cudaSuccess) { ldm_destroy(h); return fail(LDM_ERR_CUDA, "lae_table_kernel launch failed"); }
   }
   if (cudaDeviceSynchronize() != cudaSuccess) { ldm_destroy(h); return fail(LDM_ERR_CUDA, "weight packing failed: %s", cudaGetErrorString(cudaGetLastError())); }
 

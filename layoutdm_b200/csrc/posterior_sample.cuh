@@ -22,6 +22,7 @@ struct StepParams {
   int grp_start[kMaxAttr], grp_n[kMaxAttr];
   int T, t_post;
   const float* sched;                    // [G][8][T+1]
+  const float* lae;                      // [G][T+1][4] log_add_exp terms that depend on (group, t) only (lae_table_kernel)
   const float* logits; int ld_logits;    // [n_layouts*128][ld]; row = b*128 + s      (nullptr if logprob_in)
   const float* logprob_in;               // [n_layouts][S][C] or nullptr: draw from given log-probs (relation hook)
   const long long* ids_in;               // [n_layouts][S]
@@ -36,6 +37,22 @@ struct StepParams {
 LDM_DEVINL float log_add_exp(float a, float b) {   // util.py:19-21
   const float m = fmaxf(a, b);
   return m + logf(expf(a - m) + expf(b - m));
+}
+
+// The four log_add_exp terms of q_posterior that depend on (group, t) only -- computed once, with the same device function
+// the kernels use, so the group-centric kernel reads them instead of re-evaluating 2 expf + 1 logf four times per class:
+//   [0] log(q(x_t = c | x0' = c))  = lae(0      + lcat, lcbt)      [1] ... x0' != c:  lae(log eps + lcat, lcbt)
+//   [2] one-step term, same class = lae(0      + lat,  lbt)        [3] ... different: lae(log eps + lat,  lbt)
+__global__ void lae_table_kernel(const float* __restrict__ sched, float* __restrict__ lae, int G, int TT) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G * TT) return;
+  const int g = i / TT, t = i % TT;
+  const float* tab = sched + static_cast<size_t>(g) * 8 * TT;
+  const float lat = tab[0 * TT + t], lbt = tab[1 * TT + t], lcat = tab[3 * TT + t], lcbt = tab[4 * TT + t];
+  float4 o;
+  o.x = log_add_exp(0.0f + lcat, lcbt); o.y = log_add_exp(kLogEps + lcat, lcbt);
+  o.z = log_add_exp(0.0f + lat, lbt);   o.w = log_add_exp(kLogEps + lat, lbt);
+  reinterpret_cast<float4*>(lae)[i] = o;
 }
 
 // One token, every class (lane l: classes 4l..4l+3 and 128+l): any q_type, any sampling mode, log-prob in / out.
@@ -308,10 +325,10 @@ __global__ void __launch_bounds__(256) posterior_sample_group_kernel(const StepP
   const float* tab = p.sched + static_cast<size_t>(g) * 8 * (p.T + 1);
   const int t = p.t_post, tm1 = (t - 1 + (p.T + 1)) % (p.T + 1);
   const int TT = p.T + 1;
-  const float lat = tab[0 * TT + t], lbt = tab[1 * TT + t], lct = tab[2 * TT + t];
-  const float lcat = tab[3 * TT + t], lcbt = tab[4 * TT + t], lcct = tab[5 * TT + t];
+  const float lct = tab[2 * TT + t], lcct = tab[5 * TT + t];
   const float lcat1 = tab[3 * TT + tm1], lcbt1 = tab[4 * TT + tm1], lcct1 = tab[5 * TT + tm1], l1mcct1 = tab[7 * TT + tm1];
   const bool is_mask = (x_t == p.mask_id);
+  const float4 lae = __ldg(reinterpret_cast<const float4*>(p.lae) + static_cast<size_t>(g) * TT + t);
 
   // slot 0: group class gst + lane ; slot 1: PAD (lane 0) / MASK (lane 1)
   int cls[2]; bool on[2];
@@ -326,9 +343,9 @@ __global__ void __launch_bounds__(256) posterior_sample_group_kernel(const StepP
       const int c = cls[j];
       if (c != p.mask_id) {
         const float lx0 = fminf(fmaxf(static_cast<float>(static_cast<double>(__ldg(lrow + c)) - lse), -70.0f), 0.0f);
-        const float v = (c == x_t) ? 0.0f : kLogEps;
-        const float lq = is_mask ? lcct : log_add_exp(v + lcat, lcbt);
-        one[j] = is_mask ? lct : log_add_exp(v + lat, lbt);
+        const bool same = (c == x_t);
+        const float lq = is_mask ? lcct : (same ? lae.x : lae.y);          // = log_add_exp(v + lcat, lcbt), v = 0 / log eps
+        one[j] = is_mask ? lct : (same ? lae.z : lae.w);                   // = log_add_exp(v + lat, lbt)
         q[j] = lx0 - lq;
       } else {
         q[j] = kLogEps;
@@ -371,15 +388,28 @@ __global__ void __launch_bounds__(256) posterior_sample_group_kernel(const StepP
     const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
     const uint32_t tok_lo = static_cast<uint32_t>(tok), tok_hi = static_cast<uint32_t>(tok >> 32);
     const uint32_t w1 = p.step_ctr & 0xFFFFFFu;
-    auto noise_word = [&](int c, uint32_t stream) {            // class c: Philox block c / 4, word c % 4
-      const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(c) >> 2, w1 | (stream << 24), tok_lo, tok_hi), key);
-      return (c & 3) == 0 ? r.x : (c & 3) == 1 ? r.y : (c & 3) == 2 ? r.z : r.w;
-    };
-    if (p.mode == SAMP_GUMBEL) {
+    // class c draws word c % 4 of Philox block c / 4.  One evaluation per noise stream serves the whole token: lanes 0..8
+    // compute the (at most 9) blocks of the group, lanes 9 / 10 the blocks of PAD / MASK, then every lane fetches its words.
+    const int b0 = gst >> 2;
+    const int my_block = lane < 9 ? b0 + lane : (lane == 9 ? (p.pad_id >> 2) : (p.mask_id >> 2));
+    const int src0 = (cls[0] >> 2) - b0, src1 = lane == 0 ? 9 : 10;
+    auto noise_words = [&](uint32_t stream, uint32_t (&w)[2]) {
+      const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(my_block), w1 | (stream << 24), tok_lo, tok_hi), key);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        if (j == 1 && lane >= 2) continue;                     // warp-uniform per slot except the two PAD / MASK lanes
-        const float u = u01_from_bits(noise_word(cls[j], 1u));
+        const int src = j == 0 ? src0 : src1;
+        const uint32_t x = __shfl_sync(0xffffffffu, r.x, src), y = __shfl_sync(0xffffffffu, r.y, src);
+        const uint32_t z = __shfl_sync(0xffffffffu, r.z, src), ww = __shfl_sync(0xffffffffu, r.w, src);
+        const int k = cls[j] & 3;
+        w[j] = k == 0 ? x : k == 1 ? y : k == 2 ? z : ww;
+      }
+    };
+    if (p.mode == SAMP_GUMBEL) {
+      uint32_t gw[2];
+      noise_words(1u, gw);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float u = u01_from_bits(gw[j]);
         if (on[j]) lg[j] += -logf(-logf(u + 1e-30f) + 1e-30f);
       }
     }
@@ -388,12 +418,12 @@ __global__ void __launch_bounds__(256) posterior_sample_group_kernel(const StepP
 #pragma unroll
     for (int j = 0; j < 2; ++j) { ex[j] = on[j] ? expf(lg[j] - m) : 0.0f; sm += ex[j]; }
     sm = warp_sum(sm);
+    uint32_t rw[2];
+    noise_words(0u, rw);
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      score[j] = -INFINITY;
-      if (j == 1 && lane >= 2) continue;
-      const float e = -logf(u01_from_bits(noise_word(cls[j], 0u)));
-      if (on[j]) score[j] = (ex[j] / sm) / e;
+      const float e = -logf(u01_from_bits(rw[j]));
+      score[j] = on[j] ? (ex[j] / sm) / e : -INFINITY;
     }
   }
   float best = -INFINITY; int best_c = 0x7fffffff;
