@@ -105,6 +105,8 @@ def dist_setup(n_gpus):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL_DEBUG=VERSION prints a banner on stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world,
                                 device_id=torch.device("cuda", local) if torch.cuda.is_available() else None)
     return world, rank, local
