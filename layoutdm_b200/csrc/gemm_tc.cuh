@@ -73,7 +73,9 @@ struct GemmSmem {
   static_assert(kBHalfBytes % 1024 == 0, "half weight tile must keep 1024-B (swizzle atom) alignment");
   // per-epilogue-warp staging: [0,4K) 32x32 fp32 store block (128B swizzle) / 16-bit store block (64B swizzle);
   // LN: [4K,6K) 16-bit store block, [6K,10K) residual load block (128B swizzle)
-  static constexpr int kWarpStage = EPI == EPI_LN ? 10240 : (ARES ? 2048 : 4096);
+  // LN with a short ring (out-projection, K = 512): the spare shared memory holds a second private residual block [10K,14K)
+  static constexpr bool kLnExtraBuf = EPI == EPI_LN && STAGES <= 3;
+  static constexpr int kWarpStage = EPI == EPI_LN ? (kLnExtraBuf ? 14336 : 10240) : (ARES ? 2048 : 4096);
   static constexpr int kStagingBytes = 8 * kWarpStage;
   static constexpr int kBarBytes = 512;
   static constexpr int kBiasBytes = 1856 * 4;   // bias (and, for LN, gamma / beta) vectors of the layer
@@ -379,8 +381,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t sgamma_addr = sbias_addr + p.N * 4, sbeta_addr = sbias_addr + 2 * p.N * 4;
       // residual blocks (rows of 128 B, 128B swizzle): buffer 0 is private; without a y_out stream (FF2) the fp32 store
       // staging block is idle during phase A and serves as a second buffer, i.e. the loads run two chunks ahead
-      const int n_lbuf = p.y_out != nullptr ? 1 : 2;
-      const uint32_t lbuf_off[2] = {6144u, 0u};
+      const int n_lbuf = (SM::kLnExtraBuf || p.y_out == nullptr) ? 2 : 1;
+      const uint32_t lbuf_off[2] = {6144u, SM::kLnExtraBuf ? 10240u : 0u};
       uint8_t* const wbuf_ptr = smem + SM::kOffStaging + we * SM::kWarpStage;
       uint64_t* lbar = &lbars[2 * we];
       uint32_t lphase = 0;                                   // one phase bit per buffer
@@ -402,7 +404,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tma_load_2d(wbuf_ptr + lbuf_off[b], &map_resid, &lbar[b], n0 + c * 32, wrow0);
             }
           };
-          if (n_lbuf == 2 && lane == 0) bulk_wait_read0();    // the previous unit's fp32 stores have left the staging block
+          if (!SM::kLnExtraBuf && n_lbuf == 2 && lane == 0) bulk_wait_read0();    // the previous unit's fp32 stores have left the staging block
           for (int c = c_begin; c < c_begin + n_lbuf; ++c) issue_resid(c);   // in flight while the MMAs of this unit still run
           mbar_wait(&tfull[acc], acc_phase);
           tc_fence_after();
