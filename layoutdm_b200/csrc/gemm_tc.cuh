@@ -75,17 +75,20 @@ struct GemmSmem {
   // LN: [4K,6K) 16-bit store block, [6K,10K) residual load block (128B swizzle)
   // LN with a short ring (out-projection, K = 512): the spare shared memory holds a second private residual block [10K,14K)
   static constexpr bool kLnExtraBuf = EPI == EPI_LN && STAGES <= 3;
-  static constexpr int kWarpStage = EPI == EPI_LN ? (kLnExtraBuf ? 14336 : 10240) : (ARES ? 2048 : 4096);
+  // LN with a long ring (FF2, K = 1856): compact staging, the 16-bit store block [4K,6K) shares the residual block [4K,8K)
+  static constexpr bool kLnCompact = EPI == EPI_LN && STAGES >= 5;
+  static constexpr int kWarpStage = EPI == EPI_LN ? (kLnExtraBuf ? 14336 : (kLnCompact ? 8192 : 10240)) : (ARES ? 2048 : 4096);
   static constexpr int kStagingBytes = 8 * kWarpStage;
   static constexpr int kBarBytes = 512;
-  static constexpr int kBiasBytes = 1856 * 4;   // bias (and, for LN, gamma / beta) vectors of the layer
+  // bias vector of the layer; LN: bias / gamma / beta of the CTA's own column tile (a pair keeps its tile), 256 floats each
+  static constexpr int kBiasBytes = EPI == EPI_LN ? 3 * 256 * 4 : 1856 * 4;
   static constexpr int kStatBytes = EPI == EPI_LN ? 4 * kBM * 8 : 0;  // LN: per-row (sum, sumsq) partials of the two column halves, per accumulator
   static constexpr int kOffRing = kAResBytes;                      // [A-resident slots][ring stages]...
   static constexpr int kOffStaging = kOffRing + STAGES * kStageBytes;
   static constexpr int kOffBars = kOffStaging + kStagingBytes;
   static constexpr int kOffBias = kOffBars + kBarBytes;
   static constexpr int kOffStat = kOffBias + kBiasBytes;
-  static constexpr int kBytes = kOffStat + kStatBytes + 1024 /*align slack*/;
+  static constexpr int kBytes = kOffStat + kStatBytes + (kLnCompact ? 0 : 1024) /*align slack; compact: the base must be 1024-aligned (checked)*/;
   static_assert(kBytes <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
 
@@ -113,7 +116,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   static_assert(EPI != EPI_LN || (BN_STORE == 224 && UMMA_N == 240), "LN epilogue is laid out for 464 = 224 + 240 columns");
   static_assert(EPI == EPI_LN || BN_STORE == UMMA_N, "plain epilogues store whole UMMA tiles");
 
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kOffBars);
   uint64_t* full = bars;                     // leader's copy is the live one: 2 producer arrivals + both CTAs' TMA bytes
@@ -137,12 +140,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int n_super = p.M / (2 * kBM);                       // 256-row blocks
   // work units per pair: whole row blocks (inner loop over the N tiles) or, for small batches, single tiles
   const int n_outer = p.tile_sched ? n_super * p.n_tiles : n_super, n_inner = p.tile_sched ? 1 : p.n_tiles;
-  for (int i = threadIdx.x; i < p.N; i += kGemmThreads) {
-    sbias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.0f;
-    if constexpr (EPI == EPI_LN) {
-      sbias[p.N + i] = __ldg(p.ln_scale + i) + (p.adaln ? 1.0f : 0.0f);
-      sbias[2 * p.N + i] = __ldg(p.ln_shift + i);
+  if constexpr (EPI == EPI_LN) {
+    if (SM::kLnCompact && (smem_u32(smem_raw) & 1023u) != 0) { if (threadIdx.x == 0) printf("dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
+    // units o = pair + k * n_pairs with an even pair count: this pair always works on column tile (pair & 1)
+    const int tile0 = (pair & 1) * BN_STORE;
+    for (int i = threadIdx.x; i < 256; i += kGemmThreads) {
+      const int c = tile0 + i;
+      const bool ok = c < p.N;
+      sbias[i] = (ok && p.bias != nullptr) ? __ldg(p.bias + c) : 0.0f;
+      sbias[256 + i] = ok ? __ldg(p.ln_scale + c) + (p.adaln ? 1.0f : 0.0f) : 0.0f;
+      sbias[512 + i] = ok ? __ldg(p.ln_shift + c) : 0.0f;
     }
+  } else {
+    for (int i = threadIdx.x; i < p.N; i += kGemmThreads) sbias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.0f;
   }
 
   if (warp == 0 && lane == 0) {
@@ -378,11 +388,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // Every 32-column chunk goes through TMA (the last chunk of tile 1 covers columns 448..479: the TMA load zero-fills
       // and the TMA stores clip the 16 columns past N, the statistics mask them).
       float2* sstat = reinterpret_cast<float2*>(smem + SM::kOffStat);
-      const uint32_t sgamma_addr = sbias_addr + p.N * 4, sbeta_addr = sbias_addr + 2 * p.N * 4;
+      const uint32_t sgamma_addr = sbias_addr + 256 * 4, sbeta_addr = sbias_addr + 512 * 4;   // indexed by the column within the tile
       // residual blocks (rows of 128 B, 128B swizzle): buffer 0 is private; without a y_out stream (FF2) the fp32 store
       // staging block is idle during phase A and serves as a second buffer, i.e. the loads run two chunks ahead
       const int n_lbuf = (SM::kLnExtraBuf || p.y_out == nullptr) ? 2 : 1;
-      const uint32_t lbuf_off[2] = {6144u, SM::kLnExtraBuf ? 10240u : 0u};
+      const uint32_t lbuf_off[2] = {SM::kLnCompact ? 4096u : 6144u, SM::kLnExtraBuf ? 10240u : 0u};
       uint8_t* const wbuf_ptr = smem + SM::kOffStaging + we * SM::kWarpStage;
       uint64_t* lbar = &lbars[2 * we];
       uint32_t lphase = 0;                                   // one phase bit per buffer
@@ -404,7 +414,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tma_load_2d(wbuf_ptr + lbuf_off[b], &map_resid, &lbar[b], n0 + c * 32, wrow0);
             }
           };
-          if (!SM::kLnExtraBuf && n_lbuf == 2 && lane == 0) bulk_wait_read0();    // the previous unit's fp32 stores have left the staging block
+          if ((SM::kLnCompact || (!SM::kLnExtraBuf && n_lbuf == 2)) && lane == 0) bulk_wait_read0();   // the previous unit's stores have left the staging blocks the loads reuse
           for (int c = c_begin; c < c_begin + n_lbuf; ++c) issue_resid(c);   // in flight while the MMAs of this unit still run
           mbar_wait(&tfull[acc], acc_phase);
           tc_fence_after();
@@ -421,7 +431,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 rs = lds_f4(lbuf + lane * 128 + ((j ^ (lane & 7)) << 4));
-              const float4 b4 = lds_f4(sbias_addr + (n0 + c0 + 4 * j) * 4);
+              const float4 b4 = lds_f4(sbias_addr + (c0 + 4 * j) * 4);
               y[4 * j] = rs.x + b4.x; y[4 * j + 1] = rs.y + b4.y; y[4 * j + 2] = rs.z + b4.z; y[4 * j + 3] = rs.w + b4.w;
             }
             __syncwarp();                                     // every lane is done reading lbuf
@@ -489,7 +499,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tmem_wait_ld();
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) norm4(r + 4 * j, n0 + c0 + 4 * j, v + 4 * j);
+            for (int j = 0; j < 8; ++j) norm4(r + 4 * j, c0 + 4 * j, v + 4 * j);
             store_16(&map_out, v, n0 + c0, wrow0);
             if (p.out32 != nullptr) store_f32(&map_out32, v, n0 + c0, wrow0);
           }

@@ -346,7 +346,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       }
       p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch;
       ProfScope ps(h, CAT_FF2, st);
-      gemm_tc_kernel<224, 240, 4, EPI_LN, BF16><<<ln_grid, kGemmThreads, GemmSmem<240, 4, EPI_LN>::kBytes, st>>>(
+      gemm_tc_kernel<224, 240, 5, EPI_LN, BF16><<<ln_grid, kGemmThreads, GemmSmem<240, 5, EPI_LN>::kBytes, st>>>(
           h->m_hid16, h->m_w2[l], *mo, h->b_y32, h->b_x32, h->b_x32, p);
     }
     LDM_STAGE_DONE();
@@ -540,14 +540,14 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
     TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, true, true>, GemmSmem<256, 5, EPI_QKV, true>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_RELU, true, true>, GemmSmem<256, 5, EPI_RELU, true>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, true>, GemmSmem<160, 5, EPI_F32>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<224, 240, 4, EPI_LN, true>, GemmSmem<240, 4, EPI_LN>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<224, 240, 5, EPI_LN, true>, GemmSmem<240, 5, EPI_LN>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<224, 240, 3, EPI_LN, true>, GemmSmem<240, 3, EPI_LN>::kBytes)));
     TRY((set_smem(attention_kernel<true>, kAttSmemBytes)));
   } else {
     TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, false, true>, GemmSmem<256, 5, EPI_QKV, true>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_RELU, false, true>, GemmSmem<256, 5, EPI_RELU, true>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, false>, GemmSmem<160, 5, EPI_F32>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<224, 240, 4, EPI_LN, false>, GemmSmem<240, 4, EPI_LN>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<224, 240, 5, EPI_LN, false>, GemmSmem<240, 5, EPI_LN>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<224, 240, 3, EPI_LN, false>, GemmSmem<240, 3, EPI_LN>::kBytes)));
     TRY((set_smem(attention_kernel<false>, kAttSmemBytes)));
   }
