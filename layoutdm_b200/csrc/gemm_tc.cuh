@@ -4,20 +4,24 @@
 //   W : nn.Linear weight, row-major [N][K] 16-bit  (both operands are "K-major" for the MMA)
 //
 // One kernel template, launched as thread-block clusters of 2 CTAs (cta_group::2), 320 threads per CTA:
-//   warp 0     : TMA producer  (cp.async.bulk.tensor 2-D tiles, 128-byte swizzle, mbarrier complete_tx)
-//   warp 1     : TMEM allocation; in the leader CTA one thread issues tcgen05.mma for the pair (fp32 accumulators in TMEM,
-//                two accumulators so the epilogue of tile i overlaps the main loop of tile i+1)
+//   warp 0     : TMA producer  (cp.async.bulk.tensor 2-D tiles, 128-byte swizzle, mbarrier complete_tx); the warp loops
+//                warp-uniformly and one elected lane issues
+//   warp 1     : TMEM allocation; in the leader CTA it issues tcgen05.mma for the pair (fp32 accumulators in TMEM, two
+//                accumulators so the epilogue of tile i overlaps the main loop of tile i+1); warp-uniform loop, elected lane
 //   warps 2..9 : epilogue; warp w owns TMEM lanes 32*(w%4)..+31 (thread = one output row) and one half of the tile's
-//                columns.  All bulk global traffic of the epilogue goes through TMA: every warp stages 32 x 32 blocks in
+//                columns.  All global traffic of the epilogue goes through TMA: every warp stages 32 x 32 blocks in
 //                its own swizzled shared-memory buffers (conflict-free 16-byte accesses along its rows) and a single
-//                elected lane issues the tensor store / load.  A 1-CTA/SM kernel with ~200 KB of smem has no L1 and only
+//                lane issues the tensor store / load.  A 1-CTA/SM kernel with ~220 KB of smem has no L1 and only
 //                8 epilogue warps: per-thread global loads/stores made the epilogue 3-10x slower than the MMAs (profiles
-//                r01a..r01i), TMA keeps it at ~100 instructions per 32 x 32 block.
+//                r01a..r01i).
 //
+// Operand feed:  ARES (QKV, FF1; K = 464): the CTA's 128 x K activation block is resident (7 k-block tiles + a 32B-swizzled
+//                16-column tail), loaded once per row block, and only weight half-tiles stream through the ring;
+//                otherwise (out-projection, FF2, head) A tile + weight half-tile per stage.
 // Epilogues:  QKV (bias, q-scale, 16-bit) | FF1 (bias, ReLU, 16-bit) | F32 (bias; vocabulary head) |
-//             LN  (out-projection / FF2: bias + residual + LayerNorm, affine or timestep-adaptive, fused:
-//                  phase A per tile  y = acc + bias + resid -> back into TMEM (+ y_out), row sum / sum of squares,
-//                  phase B after both 232-column tiles of the row block: normalise from TMEM, 16-bit (+ fp32) outputs).
+//             LN  (out-projection / FF2: bias + residual + LayerNorm, affine or timestep-adaptive, fused; work unit =
+//                  (row block, column tile) with the row statistics exchanged between neighbouring CTA pairs -- see the
+//                  comment at the LN branch).
 //
 // Reference ops replaced: nn.Linear / nn.MultiheadAttention projections / nn.LayerNorm / AdaLayerNorm in
 // T/models/transformer_utils.py:79-83,165-210 and T/models/common/nn_lib.py:187-189,235.
@@ -41,7 +45,7 @@ struct GemmParams {
   int M, N, K;            // M multiple of 256; N = n_tiles * BN_STORE, or (non-LN) a narrower last tile: N % BN_STORE a multiple of 32
   int n_tiles;
   const float* bias;      // [N] or nullptr
-  void* out;              // remainder columns only: 16-bit [M][ldo] (QKV / RELU / LN out16) or float [M][ldo] (F32)
+  void* out;              // output tensor (informational: every store goes through the tensor maps)
   int ldo;
   float qscale;           // EPI_QKV: columns < qcols are scaled by qscale after the bias
   int qcols;
@@ -110,9 +114,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   static_assert(UMMA_N % 16 == 0 && UMMA_N <= 256 && BN_STORE <= UMMA_N, "invalid UMMA shape");
   constexpr int kAccStride = 256;            // TMEM columns between the two accumulators
   constexpr uint32_t kTmemCols = 512;
-  constexpr int kFull = BN_STORE / 32, kRem = BN_STORE % 32;
-  constexpr int kSplit = (kFull + 1) / 2;    // half 0: 32-col chunks [0, kSplit), half 1: [kSplit, kFull) + remainder
-  static_assert(kRem == 0 || kRem == 8, "unsupported tile width");
+  constexpr int kFull = BN_STORE / 32;
+  constexpr int kSplit = (kFull + 1) / 2;    // half 0: 32-col chunks [0, kSplit), half 1: [kSplit, kFull)
+  static_assert(BN_STORE % 32 == 0, "tile widths are whole 32-column chunks (every chunk leaves through TMA)");
   static_assert(EPI != EPI_LN || (BN_STORE == 224 && UMMA_N == 240), "LN epilogue is laid out for 464 = 224 + 240 columns");
   static_assert(EPI == EPI_LN || BN_STORE == UMMA_N, "plain epilogues store whole UMMA tiles");
 
@@ -340,35 +344,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           if constexpr (EPI == EPI_F32) store_f32(&map_out, v, n0 + c0, wrow0);
           else store_16(&map_out, v, n0 + c0, wrow0);
-        }
-        if constexpr (kRem == 8) {
-          if (half == 1) {                          // 8 remainder columns: direct 16 / 32-byte row stores
-            const int c0 = kFull * 32;
-            const size_t row = static_cast<size_t>(m_blk) * kBM + row_in_tile;
-            uint32_t r[32];
-            tmem_ld<8>(taddr + c0, r);
-            tmem_wait_ld();
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const float4 b4 = lds_f4(sbias_addr + (n0 + c0 + 4 * j) * 4);
-              v[4 * j] = __uint_as_float(r[4 * j]) + b4.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
-              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if constexpr (EPI == EPI_QKV) v[j] *= tile_scale;
-              if constexpr (EPI == EPI_RELU) v[j] = fmaxf(v[j], 0.0f);
-            }
-            if constexpr (EPI == EPI_F32) {
-              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row * p.ldo + n0 + c0);
-              dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-              dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-            } else {
-              *reinterpret_cast<uint4*>(static_cast<typename O::T*>(p.out) + row * p.ldo + n0 + c0) =
-                  make_uint4(O::pack(v[0], v[1]), O::pack(v[2], v[3]), O::pack(v[4], v[5]), O::pack(v[6], v[7]));
-            }
-          }
         }
         tc_fence_before();
         __syncwarp();
