@@ -283,8 +283,8 @@ __global__ void __launch_bounds__(256) posterior_sample_kernel(const StepParams 
 // Group-centric variant for the constrained (per-attribute) diffusion: outside the token's vocabulary group (plus PAD and
 // MASK) the posterior is the constant log(1e-30), so only the <= 34 classes of the group are evaluated (lane l: class
 // grp_start + l; lanes 0 / 1 additionally PAD / MASK); the float64 log-softmax still runs over all C-1 logits.
-// Preconditions (checked by the host): constrained, mode in {deterministic, random, gumbel}, no log-prob input / output, no
-// refinement table, every group <= 32 classes.  A token whose best in-group log-probability is not far enough above
+// Preconditions (checked by the host): constrained, mode in {deterministic, random, gumbel, top_p with top_p < 1}, no log-prob
+// input / output, no refinement table, every group <= 32 classes.  A token whose best in-group log-probability is not far enough above
 // log(1e-30) for the out-of-group classes to be unreachable takes posterior_token_generic instead (warp-uniform), so
 // the result is the generic kernel's in every case.
 __global__ void __launch_bounds__(256) posterior_sample_group_kernel(const StepParams p) {
@@ -384,6 +384,35 @@ __global__ void __launch_bounds__(256) posterior_sample_group_kernel(const StepP
     float lg[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) lg[j] = on[j] ? lp[j] / p.temperature : -INFINITY;
+    if (p.mode == SAMP_TOP_P) {
+      // sampling.py:94-109 restricted to the group: the classes outside it carry ~1e-30 of the mass, sit at the tail of the
+      // descending order with a cumulative mass of ~1 > top_p (the host requires top_p < 1) and are dropped in any case.
+      float m = warp_max(fmaxf(lg[0], lg[1]));
+      float pr[2], sm = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { pr[j] = on[j] ? expf(lg[j] - m) : 0.0f; sm += pr[j]; }
+      sm = warp_sum(sm);
+      pr[0] /= sm; pr[1] /= sm;
+      int n_before[2] = {0, 0};
+      double cum[2] = {static_cast<double>(pr[0]), static_cast<double>(pr[1])};
+      for (int src = 0; src < 32; ++src) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const bool on2 = jj == 0 ? src < gn : src < 2;                 // warp-uniform
+          if (!on2) continue;
+          const float v2 = __shfl_sync(0xffffffffu, lg[jj], src);
+          const float p2 = __shfl_sync(0xffffffffu, pr[jj], src);
+          const int c2 = jj == 0 ? gst + src : (src == 0 ? p.pad_id : p.mask_id);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const bool before = (v2 > lg[j]) || (v2 == lg[j] && c2 < cls[j]);   // descending sort, ties by class index
+            if (before) { n_before[j] += 1; cum[j] += static_cast<double>(p2); }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) if (on[j] && n_before[j] > 0 && static_cast<float>(cum[j]) > p.top_p) lg[j] = -INFINITY;
+    }
     const unsigned long long tok = (static_cast<unsigned long long>(p.b_global0) + b) * static_cast<unsigned long long>(p.S) + s;
     const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
     const uint32_t tok_lo = static_cast<uint32_t>(tok), tok_hi = static_cast<uint32_t>(tok >> 32);
