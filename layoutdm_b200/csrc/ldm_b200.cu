@@ -415,7 +415,7 @@ int step_impl(LdmHandle* h, int B, const long long* ids_in, int t_model, int t_p
   const int warps = B * h->S, blocks = (warps * 32 + 255) / 256;
   {
     ProfScope ps(h, CAT_EPILOGUE, st);
-    bool group_path = p.constrained && p.logprob_in == nullptr && p.logprob_out == nullptr && !(p.cond_flags & COND_REFINE) &&
+    bool group_path = p.constrained && p.logprob_in == nullptr && p.logprob_out == nullptr &&
                       (p.mode == SAMP_DETERMINISTIC || p.mode == SAMP_RANDOM || p.mode == SAMP_GUMBEL ||
                        (p.mode == SAMP_TOP_P && p.top_p < 0.9999f)) && !h->debug_generic_posterior;
     for (int g = 0; g < p.n_attr; ++g) group_path = group_path && p.grp_n[g] <= 32;

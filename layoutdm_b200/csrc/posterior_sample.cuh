@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) posterior_sample_kernel(const StepParams 
 // MASK) the posterior is the constant log(1e-30), so only the <= 34 classes of the group are evaluated (lane l: class
 // grp_start + l; lanes 0 / 1 additionally PAD / MASK); the float64 log-softmax still runs over all C-1 logits.
 // Preconditions (checked by the host): constrained, mode in {deterministic, random, gumbel, top_p with top_p < 1}, no log-prob
-// input / output, no refinement table, every group <= 32 classes.  A token whose best in-group log-probability is not far enough above
+// input / output, every group <= 32 classes.  A token whose best in-group log-probability is not far enough above
 // log(1e-30) for the out-of-group classes to be unreachable takes posterior_token_generic instead (warp-uniform), so
 // the result is the generic kernel's in every case.
 __global__ void __launch_bounds__(256) posterior_sample_group_kernel(const StepParams p) {
@@ -329,6 +329,8 @@ __global__ void __launch_bounds__(256) posterior_sample_group_kernel(const StepP
   const float lcat1 = tab[3 * TT + tm1], lcbt1 = tab[4 * TT + tm1], lcct1 = tab[5 * TT + tm1], l1mcct1 = tab[7 * TT + tm1];
   const bool is_mask = (x_t == p.mask_id);
   const float4 lae = __ldg(reinterpret_cast<const float4*>(p.lae) + static_cast<size_t>(g) * TT + t);
+  const bool refine = (p.cond_flags & COND_REFINE) && !fixed;
+  const float* trow = refine ? p.refine_tbl + static_cast<size_t>(p.cond_seq_orig[token]) * C : nullptr;
 
   // slot 0: group class gst + lane ; slot 1: PAD (lane 0) / MASK (lane 1)
   int cls[2]; bool on[2];
@@ -368,11 +370,24 @@ __global__ void __launch_bounds__(256) posterior_sample_group_kernel(const StepP
       const float ev = (cls[j] != p.mask_id) ? log_add_exp(qn + lcat1, lcbt1) : log_add_exp(qn + l1mcct1, lcct1);
       lp[j] = fminf(fmaxf((ev + one[j]) + L, -70.0f), 0.0f);
       if (fixed) lp[j] = (cls[j] == cs) ? 0.0f : kLogEps;
+      if (refine) lp[j] += __ldg(trow + cls[j]);
       if ((p.cond_flags & COND_PAD_DISABLE) && (s % p.n_attr != 0) && cs != p.pad_id && cls[j] == p.pad_id) lp[j] = kLogEps;
       lmax = fmaxf(lmax, lp[j]);
     }
   }
   lmax = warp_max(lmax);
+  if (refine) {
+    // the refinement prior (task.py:154-224: lambda on the token's own attribute band) must not lift a class outside the group
+    // above log(1e-30); a caller-supplied table that does sends the token to the all-classes routine
+    float tmax = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int c = j < 4 ? 4 * lane + j : 128 + lane;
+      const bool in_grp = (c >= gst && c < gst + gn) || c == p.pad_id || c == p.mask_id;
+      if (c < C && !in_grp) tmax = fmaxf(tmax, __ldg(trow + c));
+    }
+    if (warp_max(tmax) > 0.0f) { posterior_token_generic(p, token, lane); return; }
+  }
   // every class outside the group sits at log(1e-30): it must be out of reach of the draw (see the header comment)
   const float margin = p.mode == SAMP_DETERMINISTIC ? 0.0f : 40.0f * p.temperature;
   if (!(lmax - kLogEps > margin)) { posterior_token_generic(p, token, lane); return; }
