@@ -49,7 +49,7 @@ struct GemmParams {
   int ldo;
   float qscale;           // EPI_QKV: columns < qcols are scaled by qscale after the bias
   int qcols;
-  // EPI_LN (N = 464 = 2 tiles of 232): y = acc + bias + resid ; out = LayerNorm(y) * gamma + beta  (gamma = 1 + scale_t for AdaLN)
+  // EPI_LN (N = 464 = column tiles of 224 + 240): y = acc + bias + resid ; out = LayerNorm(y) * gamma + beta  (gamma = 1 + scale_t for AdaLN)
   const float* resid;     // fp32 [M][N] residual stream
   float* y_out;           // fp32 [M][N] pre-norm sum (the next residual) or nullptr
   const float* ln_scale;  // [N]

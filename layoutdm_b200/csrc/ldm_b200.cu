@@ -39,7 +39,7 @@ constexpr int kHeadPad = 64;        // per-head width after padding 58 -> 64
 constexpr int kQkvN = 3 * 8 * kHeadPad;   // 1536
 constexpr int kAttN = 8 * kHeadPad;        // 512: attention output, heads padded like Q/K/V
 constexpr int kLogitLd = 160;       // padded logits row (C <= 160)
-constexpr int kFF1Tile = 232;       // FF1 N tile (1856 = 8 * 232), computed as UMMA_N = 240
+constexpr int kDModel = 464;        // the kernels are laid out for the paper's backbone: d = 464 (LN tiles 224 + 240), ff = 4 d
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -320,7 +320,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     }
     LDM_STAGE_DONE();
     {  // out-projection + bias + residual (from the NORMALISED x) -> y32 ; z16 = LayerNorm2(y)   [fused epilogue]
-      GemmParams p{M, d, kAttN, d / kFF1Tile, h->bo[l], h->z16, d, 1.0f, 0, h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr};
+      GemmParams p{M, d, kAttN, 2, h->bo[l], h->z16, d, 1.0f, 0, h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr};
       p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch;
       ProfScope ps(h, CAT_OUTPROJ, st);
       gemm_tc_kernel<224, 240, 3, EPI_LN, BF16><<<ln_grid, kGemmThreads, GemmSmem<240, 3, EPI_LN>::kBytes, st>>>(
@@ -336,7 +336,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     }
     LDM_STAGE_DONE();
     {  // FF2 + bias + residual ; next block's AdaLN(h, t) (fp32 residual + 16-bit operand) or the head LayerNorm   [fused epilogue]
-      GemmParams p{M, d, ff, d / kFF1Tile, h->b2[l], nullptr, d, 1.0f, 0, h->y32, nullptr, nullptr, nullptr, 0, nullptr};
+      GemmParams p{M, d, ff, 2, h->b2[l], nullptr, d, 1.0f, 0, h->y32, nullptr, nullptr, nullptr, 0, nullptr};
       const CUtensorMap* mo = &h->b_z16;
       if (l + 1 < L) {
         const float* tab = h->adaln + (static_cast<size_t>(l + 1) * T + t_model) * 2 * d;
@@ -437,7 +437,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   if (!desc || !w || !out) return fail(LDM_ERR_INVALID, "null argument");
   const int d = desc->d_model, ff = desc->d_ff, L = desc->n_layers, T = desc->num_timesteps;
   const int C = desc->n_cat + 4 * desc->n_bins + 2, S = desc->n_elem * desc->n_attr;
-  if (d != 2 * kFF1Tile || desc->n_heads != 8 || ff != 8 * kFF1Tile)
+  if (d != kDModel || desc->n_heads != 8 || ff != 4 * kDModel)
     return fail(LDM_ERR_UNSUPPORTED, "kernels are built for d_model=464, 8 heads, d_ff=1856 (got %d, %d, %d)", d, desc->n_heads, ff);
   if (L < 1 || L > kMaxLayers || T < 2) return fail(LDM_ERR_UNSUPPORTED, "n_layers must be in [1,%d], T >= 2", kMaxLayers);
   if (C < 129 || C > kLogitLd || S > 125 || S < 1 || desc->n_attr > kMaxAttr || desc->n_attr < 1)
