@@ -226,6 +226,18 @@ struct ProfScope {   // counts the launch; when profiling is on, brackets it wit
   ~ProfScope() { if (b) cudaEventRecord(b, st); }
 };
 
+// Cooperative launch: every CTA of the grid is guaranteed to be resident at the same time (or the launch fails).  The LN GEMMs
+// need it: neighbouring CTA pairs exchange row statistics while both are running (gemm_tc.cuh).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_cooperative(void (*kernel)(KArgs...), int grid, int block, int smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 template <typename K>
 int set_smem(K kernel, int bytes) {
   CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -323,8 +335,8 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       GemmParams p{M, d, kAttN, 2, h->bo[l], h->z16, d, 1.0f, 0, h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr};
       p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch;
       ProfScope ps(h, CAT_OUTPROJ, st);
-      gemm_tc_kernel<224, 240, 3, EPI_LN, BF16><<<ln_grid, kGemmThreads, GemmSmem<240, 3, EPI_LN>::kBytes, st>>>(
-          h->m_att16, h->m_wo[l], h->b_z16, h->b_x32, h->b_y32, h->b_y32, p);
+      CK(launch_cooperative(gemm_tc_kernel<224, 240, 3, EPI_LN, BF16>, ln_grid, kGemmThreads, GemmSmem<240, 3, EPI_LN>::kBytes, st,
+                            h->m_att16, h->m_wo[l], h->b_z16, h->b_x32, h->b_y32, h->b_y32, p));
     }
     LDM_STAGE_DONE();
     {  // FF1 + ReLU
@@ -346,8 +358,8 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       }
       p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch;
       ProfScope ps(h, CAT_FF2, st);
-      gemm_tc_kernel<224, 240, 5, EPI_LN, BF16><<<ln_grid, kGemmThreads, GemmSmem<240, 5, EPI_LN>::kBytes, st>>>(
-          h->m_hid16, h->m_w2[l], *mo, h->b_y32, h->b_x32, h->b_x32, p);
+      CK(launch_cooperative(gemm_tc_kernel<224, 240, 5, EPI_LN, BF16>, ln_grid, kGemmThreads, GemmSmem<240, 5, EPI_LN>::kBytes, st,
+                            h->m_hid16, h->m_w2[l], *mo, h->b_y32, h->b_x32, h->b_x32, p));
     }
     LDM_STAGE_DONE();
   }
