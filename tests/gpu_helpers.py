@@ -20,10 +20,13 @@ def debug_read(engine, name: str, n_layouts: int) -> torch.Tensor:
 
 
 def unpack_qkv(qkv: torch.Tensor, S: int = 125, heads: int = 8, dh: int = 58):
-    """[B,128,1536] padded per-head layout -> q,k,v each (B,H,S,dh) and the max |value| found in the padding columns"""
+    """[B,128,1536] padded per-head layout -> q,k,v each (B,H,S,dh) and the max deviation of the padding columns from their
+    contract: zeros, except column dh of every V head, which is 1.0 (the softmax-denominator column, attention.cuh)"""
     B = qkv.shape[0]
-    x = qkv[:, :S].view(B, S, 3, heads, 64)
-    pad = x[..., dh:].abs().max().item()
+    x = qkv[:, :S].view(B, S, 3, heads, 64).float()
+    want = torch.zeros_like(x[..., dh:])
+    want[:, :, 2, :, 0] = 1.0
+    pad = (x[..., dh:] - want).abs().max().item()
     q, k, v = (x[:, :, i, :, :dh].permute(0, 2, 1, 3).contiguous() for i in range(3))
     return q, k, v, pad
 
