@@ -145,6 +145,17 @@ int ldm_q_sample(LdmHandle* h, int32_t B, const int64_t* x0_ids_dev, const int32
 int ldm_decode(LdmHandle* h, int32_t B, const int64_t* ids_dev, const float* centers_dev, float* bbox_out_dev,
                int64_t* label_out_dev, uint8_t* mask_out_dev, void* stream);
 
+/* layouts -> cond on the device == LayoutSequenceTokenizer.encode (layout_tokenizer.py:208-253) + BboxTokenizer.encode
+ * (bbox_tokenizer.py:86-114) + get_cond (helpers/task.py:27-151) for the deterministic types:
+ *   cond_type 0 = "c" (:94-110), 1 = "cwh" (:94-110), 2 = "refinement" (:126-140; bbox_dev already carries the caller's
+ *   N(0, 0.1) perturbation of :127), 3 = "gt" (:116-117).  "partial" / "random" draw host random numbers and stay in Python.
+ * Inputs (device): label [B][n_elem] i64, bbox [B][n_elem][4] f32 xywh, elem_mask [B][n_elem] u8 (valid elements first),
+ * centers_dev [4][n_bins] cluster centres or NULL for linear bins.  Outputs (device): seq [B][S] i64, mask [B][S] u8
+ * (1 = fixed token), seq_orig [B][S] i64 (refinement only, else may be NULL) -- exactly the LdmCond fields. */
+int ldm_make_cond(LdmHandle* h, int32_t B, int32_t cond_type, const int64_t* label_dev, const float* bbox_dev,
+                  const uint8_t* elem_mask_dev, const float* centers_dev, int64_t* seq_out_dev, uint8_t* mask_out_dev,
+                  int64_t* seq_orig_out_dev, void* stream);
+
 /* Introspection */
 int64_t ldm_launch_count(const LdmHandle* h);            /* kernels launched by this handle so far */
 int32_t ldm_num_classes(const LdmHandle* h);             /* C */

@@ -49,6 +49,8 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ldm_q_sample": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]),
     "ldm_decode": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldm_make_cond": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p]),
     "ldm_launch_count": (C.c_int64, [C.c_void_p]),
     "ldm_num_classes": (C.c_int32, [C.c_void_p]),
     "ldm_seq_len": (C.c_int32, [C.c_void_p]),

@@ -706,6 +706,29 @@ int ldm_decode(LdmHandle* h, int32_t B, const int64_t* ids, const float* centers
   return LDM_OK;
 }
 
+int ldm_make_cond(LdmHandle* h, int32_t B, int32_t cond_type, const int64_t* label, const float* bbox, const uint8_t* elem_mask,
+                  const float* centers, int64_t* seq, uint8_t* mask, int64_t* seq_orig, void* stream) {
+  if (!h || !label || !bbox || !elem_mask || !seq || !mask || B <= 0) return fail(LDM_ERR_INVALID, "bad ldm_make_cond arguments");
+  if (h->desc.n_attr != 5) return fail(LDM_ERR_UNSUPPORTED, "make_cond needs the c-x-y-w-h token layout");
+  if (cond_type < COND_TYPE_C || cond_type > COND_TYPE_GT)
+    return fail(LDM_ERR_UNSUPPORTED, "cond_type %d: only c / cwh / refinement / gt are built on the device (task.py:27-151 raises NotImplementedError for unknown types)", cond_type);
+  if (cond_type == COND_TYPE_REFINEMENT && !seq_orig) return fail(LDM_ERR_INVALID, "refinement needs seq_orig_out");
+  CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = B * h->desc.n_elem;
+  const double dd = 1.0 / h->desc.n_bins;
+  {
+    ProfScope ps(h, CAT_MISC, st);
+    make_cond_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(label), bbox, elem_mask, centers,
+                                                     reinterpret_cast<long long*>(seq), mask,
+                                                     cond_type == COND_TYPE_REFINEMENT ? reinterpret_cast<long long*>(seq_orig) : nullptr, B,
+                                                     h->desc.n_elem, h->desc.n_cat, h->desc.n_bins, h->C - 2, h->C - 1, cond_type,
+                                                     static_cast<float>(dd), static_cast<float>(1.0 - dd));
+  }
+  CK(cudaGetLastError());
+  return LDM_OK;
+}
+
 int64_t ldm_launch_count(const LdmHandle* h) { return h ? h->launches : 0; }
 
 int ldm_profile_begin(LdmHandle* h) {

@@ -565,4 +565,57 @@ __global__ void decode_kernel(const long long* __restrict__ ids, const float* __
   mask[i] = valid ? 1 : 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// layouts -> ids -> cond on the device: LayoutSequenceTokenizer.encode (T/helpers/layout_tokenizer.py:208-253, :96-104) +
+// BboxTokenizer.encode (T/helpers/bbox_tokenizer.py:86-114) + the deterministic branches of get_cond (T/helpers/task.py:94-110
+// c / cwh, :116-117 gt, :126-140 refinement with the caller's perturbed boxes).  One thread per element.
+enum : int { COND_TYPE_C = 0, COND_TYPE_CWH = 1, COND_TYPE_REFINEMENT = 2, COND_TYPE_GT = 3 };
+
+__global__ void make_cond_kernel(const long long* __restrict__ label /*[B][E]*/, const float* __restrict__ bbox /*[B][E][4]*/,
+                                 const unsigned char* __restrict__ elem_mask /*[B][E]*/, const float* __restrict__ centers /*[4][n_bins] or null*/,
+                                 long long* __restrict__ seq /*[B][E*5]*/, unsigned char* __restrict__ mask /*[B][E*5]*/,
+                                 long long* __restrict__ seq_orig /*[B][E*5] or null*/, int n_layouts, int n_elem, int n_cat, int n_bins,
+                                 int pad_id, int mask_id, int cond_type, float d32 /*float(1/n_bins)*/, float hi32 /*float(1 - 1/n_bins)*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_layouts * n_elem) return;
+  const bool valid = elem_mask[i] != 0;
+  long long tok[5];
+  tok[0] = label[i];
+  const float4 bb = reinterpret_cast<const float4*>(bbox)[i];
+  const float v[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    int bin;
+    if (centers == nullptr) {
+      // float32 like torch: clamp, (w, h: - d), * n_bins, round half to even (bbox_tokenizer.py:90-93)
+      const float q = a < 2 ? fminf(fmaxf(v[a], 0.0f), hi32) : __fsub_rn(fminf(fmaxf(v[a], d32), 1.0f), d32);
+      bin = __float2int_rn(__fmul_rn(static_cast<float>(n_bins), q));
+    } else {
+      // nearest cluster centre, first index on ties (KMeans.predict, :95-104)
+      float best = INFINITY; bin = 0;
+      for (int k = 0; k < n_bins; ++k) {
+        const float df = __fsub_rn(v[a], centers[a * n_bins + k]);
+        const float dist = __fmul_rn(df, df);
+        if (dist < best) { best = dist; bin = k; }
+      }
+    }
+    tok[1 + a] = static_cast<long long>(bin) + static_cast<long long>(a) * n_bins + n_cat;
+  }
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    const long long t = valid ? tok[a] : pad_id;                          // _fix_padded_sequences
+    bool keep;
+    if (cond_type == COND_TYPE_C) keep = a == 0;
+    else if (cond_type == COND_TYPE_CWH) keep = a == 0 || a == 3 || a == 4;
+    else if (cond_type == COND_TYPE_REFINEMENT) keep = a == 0;
+    else keep = true;
+    long long s = keep ? t : mask_id;
+    if (!valid) s = pad_id;
+    const size_t o = static_cast<size_t>(i) * 5 + a;
+    seq[o] = s;
+    mask[o] = cond_type == COND_TYPE_GT ? (valid ? 1 : 0) : ((valid && keep) || !valid ? 1 : 0);
+    if (seq_orig != nullptr) seq_orig[o] = t;
+  }
+}
+
 }  // namespace ldm

@@ -196,6 +196,15 @@ class LayoutDMB200:
             return {k: v.cpu() for k, v in self.model.engine.decode(ids, c).items()}
         return decode_ids(ids, self.vocab, self._centers)
 
+    def get_cond(self, label: torch.Tensor, bbox: torch.Tensor, mask: torch.Tensor, cond_type: str = "c", refine: Optional[dict] = None) -> Dict:
+        """helpers/task.py:get_cond (:27-151) for dense layouts (what `sparse_to_dense(batch)` returns: bbox (B,E,4), label (B,E),
+        mask (B,E)), built on the GPU for cond_type c / cwh / gt / refinement; for refinement the N(0, 0.1) box noise of
+        task.py:127 is drawn here from torch's global generator, like the reference does."""
+        if cond_type == "refinement":
+            bbox = bbox + torch.normal(0, std=0.1, size=bbox.size())
+        c = None if self._centers is None else torch.stack([torch.as_tensor(x, dtype=torch.float32).view(-1) for x in self._centers])
+        return self.model.engine.cond_from_layouts(label, bbox, mask, cond_type, centers=c, refine=refine)
+
     def aggregate_sampling_settings(self, sampling_cfg, args):
         """base_model.py:124-150 + layoutdm.py:90-97"""
         if args.cond == "refinement" and args.refine_lambda > 0.0:

@@ -8,7 +8,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from .vocab import Vocab
+from .vocab import Vocab, linear_centers, refinement_table
 
 PREFIXES = ("model.module.transformer.", "model.transformer.", "module.transformer.", "transformer.", "")
 
@@ -214,6 +214,39 @@ class Engine:
         c = None if centers is None else centers.to(self.device, torch.float32).contiguous()
         _lib.check(self.lib.ldm_decode(self._h, B, _ptr(ids), _ptr(c), _ptr(bbox), _ptr(label), _ptr(mask), self._stream()))
         return {"bbox": bbox, "label": label, "mask": mask.bool()}
+
+    COND_TYPES = {"c": 0, "cwh": 1, "refinement": 2, "gt": 3}
+
+    def cond_from_layouts(self, label: torch.Tensor, bbox: torch.Tensor, mask: torch.Tensor, cond_type: str = "c",
+                          centers: Optional[torch.Tensor] = None, refine: Optional[dict] = None) -> dict:
+        """get_cond (helpers/task.py:27-151) on the device for cond_type c / cwh / refinement / gt: dense layouts
+        (label (B,E) i64, bbox (B,E,4) f32 xywh, mask (B,E) bool with the valid elements first) -> the `cond` dict `sample()`
+        takes, tensors on the GPU.  For "refinement" `bbox` must already carry the N(0, 0.1) perturbation of task.py:127;
+        `refine` (refine_mode / refine_offset_ratio / refine_lambda, hydra_configs.py:39-41) builds the band table."""
+        if cond_type not in self.COND_TYPES:
+            raise NotImplementedError(f"cond_type {cond_type!r} is built on the host (task.py)")
+        B, E = label.shape
+        assert E == self.vocab.n_elem and bbox.shape == (B, E, 4) and mask.shape == (B, E)
+        lab = label.to(self.device, torch.int64).contiguous()
+        bb = bbox.to(self.device, torch.float32).contiguous()
+        em = mask.to(self.device).to(torch.uint8).contiguous()
+        c = None if centers is None else centers.to(self.device, torch.float32).contiguous()
+        S = self.vocab.S
+        seq = torch.empty(B, S, dtype=torch.int64, device=self.device)
+        m = torch.empty(B, S, dtype=torch.uint8, device=self.device)
+        so = torch.empty(B, S, dtype=torch.int64, device=self.device) if cond_type == "refinement" else None
+        _lib.check(self.lib.ldm_make_cond(self._h, B, self.COND_TYPES[cond_type], _ptr(lab), _ptr(bb), _ptr(em), _ptr(c), _ptr(seq),
+                                          _ptr(m), _ptr(so), self._stream()))
+        cond = {"seq": seq, "mask": m.bool(), "type": cond_type}
+        if cond_type != "gt":
+            cond["num_element"] = em.sum(dim=1, dtype=torch.int64)
+        if cond_type == "refinement":
+            r = dict(refine_mode="uniform", refine_offset_ratio=0.1, refine_lambda=3.0)
+            r.update(refine or {})
+            cen = linear_centers(self.vocab.n_bins) if centers is None else [row.numpy() for row in centers.detach().cpu().double()]
+            cond["seq_orig"] = so
+            cond["refine_table"] = refinement_table(self.vocab, cen, r["refine_mode"], r["refine_offset_ratio"], r["refine_lambda"]).to(self.device)
+        return cond
 
     def sample_host(self, B: int, plan, sampling, cond: Optional[dict] = None, seed: int = 0, b_global0: int = 0,
                     ids_init: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):

@@ -561,6 +561,63 @@ def decode_ids(ids: torch.Tensor, vocab: VocabSpec) -> Dict[str, torch.Tensor]:
 
 
 # --------------------------------------------------------------------------------------------------------------
+# layouts -> ids -> cond  (tokenizer.encode layout_tokenizer.py:208-253 + bbox_tokenizer.py:86-114; get_cond task.py:27-151)
+# --------------------------------------------------------------------------------------------------------------
+
+
+def encode_layouts(label: torch.Tensor, bbox: torch.Tensor, mask: torch.Tensor, vocab: VocabSpec,
+                   centers: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """LayoutSequenceTokenizer.encode for var_order c-x-y-w-h, shared_bbox_vocab x-y-w-h, pad_until_max, no BOS/EOS, no sort:
+    label (B,E) i64, bbox (B,E,4) f32 xywh, mask (B,E) bool (valid elements form a prefix) -> seq (B,S) i64, mask (B,S) bool.
+    Linear quantisation: bbox_tokenizer.py:90-93 (float32 clamp / subtract / multiply, torch.round = half-to-even);
+    centers (4, n_bins) f32 = kmeans / percentile cluster centres: nearest centre like KMeans.predict (:95-104)."""
+    B, E = label.shape
+    nb = vocab.n_bins
+    bbox = bbox.float()
+    if centers is None:
+        d = 1 / nb
+        q = torch.zeros_like(bbox)
+        q[..., :2] = torch.clamp(bbox[..., :2], 0.0, 1.0 - d)
+        q[..., 2:] = torch.clamp(bbox[..., 2:], d, 1.0) - d
+        idx = (nb * q).round().long()
+    else:
+        dist = (bbox[..., None] - centers.float()[None, None]) ** 2          # (B,E,4,nb)
+        idx = dist.argmin(dim=-1)
+    idx = idx + torch.arange(4) * nb + vocab.n_cat                            # KEY_MULT x-y-w-h offsets (:107-109) + :223
+    tok = torch.cat([label[..., None], idx], dim=-1)                          # (B,E,5)
+    tok[~mask] = vocab.pad_id                                                 # _fix_padded_sequences :96-104
+    return tok.reshape(B, E * vocab.n_attr), mask[..., None].expand(B, E, vocab.n_attr).reshape(B, E * vocab.n_attr)
+
+
+def make_cond(label: torch.Tensor, bbox: torch.Tensor, mask: torch.Tensor, vocab: VocabSpec, cond_type: str,
+              centers: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """get_cond (task.py:27-151) for the deterministic conditioning types, model_type="LayoutDM":
+    c / cwh (:94-110), gt (:116-117), refinement (:126-140; `bbox` is the already perturbed box, the caller draws the
+    N(0, 0.1) noise of :127).  `partial` / `random` draw host random numbers and stay in Python."""
+    seq, m = encode_layouts(label, bbox, mask, vocab, centers)
+    attr = torch.arange(vocab.S)[None] % vocab.n_attr
+    out: Dict[str, torch.Tensor] = {}
+    if cond_type in ("c", "cwh"):
+        keep = attr == 0 if cond_type == "c" else ((attr == 0) | (attr == 3) | (attr == 4))
+        s2 = torch.where(keep, seq, torch.full_like(seq, vocab.mask_id))
+        s2 = torch.where(m, s2, torch.full_like(seq, vocab.pad_id))
+        out = {"seq": s2, "mask": (m & keep) | ~m}
+    elif cond_type == "gt":
+        out = {"seq": seq, "mask": m}
+    elif cond_type == "refinement":
+        cm = (m & (attr == 0)) | ~m
+        s2 = torch.where(cm, seq, torch.full_like(seq, vocab.mask_id))
+        s2 = torch.where(m, s2, torch.full_like(seq, vocab.pad_id))
+        out = {"seq": s2, "mask": cm, "seq_orig": seq}
+    else:
+        raise NotImplementedError(cond_type)
+    out["type"] = cond_type
+    if cond_type in ("c", "cwh", "refinement"):
+        out["num_element"] = mask.sum(dim=1)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
 # forward (corruption) process on ids  (constrained.py:208-230, vanilla.py:153-158; used by training forward :232-260)
 # --------------------------------------------------------------------------------------------------------------
 

@@ -300,3 +300,40 @@ def test_decode_kernel_matches_host_decode():
     centers = torch.stack([torch.as_tensor(c, dtype=torch.float32) for c in linear_centers(32)])
     got2 = {k: v.cpu() for k, v in eng.decode(ids.cuda(), centers).items()}
     assert torch.allclose(got2["bbox"], want["bbox"], atol=1e-6) and torch.equal(got2["mask"], want["mask"])
+
+
+@pytest.mark.parametrize("cond_type", ["c", "cwh", "gt", "refinement"])
+def test_make_cond_kernel_matches_oracle(cond_type):
+    """layouts -> cond on the device (ldm_make_cond) == the oracle's restatement of tokenizer.encode + get_cond, which is pinned
+    against the reference in tests/test_oracle_vs_reference.py; ids are bit-exact (linear bins incl. the .5 rounding boundaries
+    and boxes outside [0, 1]; cluster centres), and the result drives sample() with the strong mask reproduced."""
+    fx = Fixture("rico25_uncond_random")
+    eng = engine_for(fx)
+    vocab = fx.vocab
+    B, E = 37, vocab.n_elem
+    g = torch.Generator().manual_seed(5)
+    n_el = torch.randint(1, E + 1, (B,), generator=g)
+    n_el[0], n_el[1] = E, 1
+    mask = torch.arange(E)[None] < n_el[:, None]
+    label = torch.randint(0, vocab.n_cat, (B, E), generator=g)
+    bbox = torch.rand(B, E, 4, generator=g) * 1.3 - 0.15
+    bbox[::5] = (torch.arange(bbox[::5].numel()).view(bbox[::5].shape) % 33).float() / 32.0 + 1.0 / 64.0   # exact .5 boundaries
+    want = O.make_cond(label, bbox, mask, vocab, cond_type)
+    got = eng.cond_from_layouts(label, bbox, mask, cond_type)
+    keys = ("seq", "mask") + (("seq_orig",) if cond_type == "refinement" else ())
+    for k in keys:
+        assert torch.equal(got[k].cpu(), want[k]), k
+    if cond_type != "gt":
+        assert torch.equal(got["num_element"].cpu(), want["num_element"])
+    # cluster centres (kmeans / percentile quantisation): nearest centre
+    centers = torch.sort(torch.rand(4, vocab.n_bins, generator=g), dim=1).values
+    want_c = O.make_cond(label, bbox, mask, vocab, cond_type, centers=centers)
+    got_c = eng.cond_from_layouts(label, bbox, mask, cond_type, centers=centers)
+    for k in keys:
+        assert torch.equal(got_c[k].cpu(), want_c[k]), k
+    if cond_type in ("c", "cwh", "refinement"):
+        from layoutdm_b200 import timestep_plan
+        ids = eng.sample_loop(B, timestep_plan(fx.spec.T, 10), {"name": "random", "temperature": 1.0}, cond=got, seed=3, ids_init=got["seq"])
+        assert torch.equal(ids[got["mask"]], got["seq"][got["mask"]])
+    with pytest.raises(NotImplementedError):
+        eng.cond_from_layouts(label, bbox, mask, "partial")

@@ -58,3 +58,27 @@ def test_decode_matches_reference_tokenizer(ref):
     a, b = tok.decode(ids.clone()), O.decode_ids(ids, vocab)
     for k in ("bbox", "label", "mask"):
         assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("cond_type", ["c", "cwh", "gt", "refinement"])
+def test_make_cond_matches_reference_get_cond(ref, cond_type):
+    """cond construction: oracle.make_cond == the reference's get_cond (task.py:27-151) on a fake PyG batch, incl.
+    boxes outside [0, 1] and on the rounding boundaries of the linear quantisation"""
+    model, tok, vocab = ref
+    rh._setup_path()
+    from trainer.data.util import sparse_to_dense
+    from trainer.helpers.task import get_cond
+    batch = rh.synthetic_layouts(48, vocab.n_cat, seed=3)
+    batch.x = batch.x * 1.3 - 0.15                              # some coordinates below 0 / above 1
+    batch.x[::7] = (torch.arange(batch.x[::7].numel()).view(-1, 4) % 33).float() / 32.0 + 1.0 / 64.0   # exact .5 bin boundaries
+    bbox, label, _, mask = sparse_to_dense(batch)
+    torch.manual_seed(11)
+    want = get_cond(batch, tok, cond_type=cond_type, model_type="LayoutDM")
+    if cond_type == "refinement":
+        torch.manual_seed(11)
+        bbox = bbox + torch.normal(0, std=0.1, size=bbox.size())   # the draw of task.py:127
+    got = O.make_cond(label, bbox, mask, vocab, cond_type)
+    for k in ("seq", "mask") + (("seq_orig",) if cond_type == "refinement" else ()):
+        assert torch.equal(want[k], got[k]), k
+    if cond_type != "gt":
+        assert torch.equal(want["num_element"], got["num_element"])
