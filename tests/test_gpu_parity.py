@@ -264,6 +264,16 @@ def test_class_api_mirror():
     assert nxt.shape == (2, 155, 125)
     with pytest.raises(AssertionError):      # base.py:311
         core.sample(batch_size=1, sampling_cfg={"name": "random", "num_timesteps": 101})
+    # get_cond -> sample, both on the device: label-conditioned generation keeps the given labels / element counts
+    g = torch.Generator().manual_seed(1)
+    n_el = torch.tensor([25, 1, 7])
+    mask = torch.arange(25)[None] < n_el[:, None]
+    label = torch.randint(0, 25, (3, 25), generator=g)
+    cond = model.get_cond(label, torch.rand(3, 25, 4, generator=g), mask, cond_type="c")
+    out3 = model.sample(batch_size=3, cond=cond, sampling_cfg={"name": "random", "temperature": 1.0, "num_timesteps": 20}, cond_type="c")
+    assert torch.equal(out3["mask"], mask) and torch.equal(out3["label"][mask], label[mask])
+    cond_r = model.get_cond(label, torch.rand(3, 25, 4, generator=g), mask, cond_type="refinement")
+    assert set(cond_r) >= {"seq", "mask", "seq_orig", "refine_table", "num_element", "type"}
 
 
 def test_q_sample_kernel_matches_oracle():
