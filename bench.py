@@ -8,8 +8,9 @@ A "step" is one full pass of the hot path over one batch: `sample()` of B=1024 l
 denoising iterations (BASELINE.json configs[1]: rico25 unconditional, T=100, batch 1024, random sampling).
 Prints ONE JSON line (rank 0).  `value` = layouts/s with everything device-resident; `e2e` = the same metric through
 the host-buffer C-ABI entry (ldm_sample_host: pinned-host inputs -> H2D -> loop -> D2H of the ids);
-`roofline` = the dominant kernel against the measured bf16 tensor peak; `cpu_baseline` = the oracle port of the
-reference's CPU path on a bounded sample.  `--impl reference` times that CPU path alone.
+`roofline` = the dominant kernel against the measured bf16 tensor peak; `cpu_baseline` = the unmodified reference's
+`LayoutDM.sample` on the host cores (bounded sample; packaged by oracle/make_ref.py), `gpu_eager_baseline` = the same
+reference run eagerly on the GPU.  `--impl reference` times the CPU reference alone.
 """
 from __future__ import annotations
 
@@ -128,64 +129,124 @@ def max_over_ranks(x: float, world, device):
 
 
 # --------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's algorithm on the host cores (oracle port; the reference itself is Python and lives in
-# /root/reference, which does not exist on the GPU box)
+# Reference arm: the UNMODIFIED reference `LayoutDM.sample` (layoutdm.py:77-88 -> base.py:293-371) from the archive
+# oracle/make_ref.py packaged (oracle/_ref/trainer_ref.zip; /root/reference does not exist on the GPU box), on the host
+# cores.  Falls back to the oracle port (kind "port") only if the archive is missing.
 # --------------------------------------------------------------------------------------------------------------
-def cpu_pass(orc, O, B, timesteps, seed):
-    """runs `len(timesteps)` of the T denoising iterations for B layouts; returns seconds"""
-    vo = orc.vocab
-    x = torch.full((B, vo.S), vo.mask_id, dtype=torch.long)
-    cfg = O.SamplingCfg(name="random")
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        for i, t in enumerate(timesteps):
-            lp, _ = orc.step_logprob(x, t, t)
-            x = O.draw(lp, cfg, O.uniforms(seed, i, 0, 0, B, vo.S, vo.C))
-    return time.perf_counter() - t0
+REF_B, REF_NT = 64, 8        # fixed bounded sample: 64 layouts x 8 of the T=100 denoising iterations per step (B=64 is the
+                             # reference's most efficient CPU batch per layout: measured 64x8 / 256x2 / 512x1 -> 1.96 / 1.28 / 1.12 layouts/s on 8 cores)
 
 
-def make_cpu_oracle():
-    from oracle import layoutdm_oracle as O          # allowed here: cpu_baseline / --impl reference legs only
-    from layoutdm_b200 import Vocab
-    from layoutdm_b200.synthetic import random_state_dict
-    sd = random_state_dict(Vocab.for_dataset("rico25"), num_timesteps=T, seed=0)
-    return O.Oracle(O.RICO25, O.ModelSpec(T=T), sd), O
+def physical_cores(cap=64):
+    """physical cores this process may run on (SMT siblings counted once), capped"""
+    aff = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else set(range(os.cpu_count() or 1))
+    cores = set()
+    try:
+        cpu = phys = core = None
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("processor"):
+                cpu = int(line.split(":")[1])
+            elif line.startswith("physical id"):
+                phys = int(line.split(":")[1])
+            elif line.startswith("core id"):
+                core = int(line.split(":")[1])
+            elif not line.strip():
+                if cpu in aff and phys is not None and core is not None:
+                    cores.add((phys, core))
+                cpu = phys = core = None
+    except Exception:
+        pass
+    n = len(cores) if cores else len(aff)
+    return max(1, min(n, cap))
 
 
-def cpu_sample_plan(budget_s, orc, O):
-    """pick (B_s, n_t) so that one bounded sample costs about budget_s seconds"""
-    B_s = 64
-    t1 = cpu_pass(orc, O, B_s, [50], 0)               # calibration (also warms the thread pool)
-    t1 = min(t1, cpu_pass(orc, O, B_s, [50], 0))
-    n_t = int(max(1, min(T, budget_s / max(t1, 1e-3))))
-    return B_s, n_t, t1
+class CpuArm:
+    """one `step` = sample() of REF_B layouts through REF_NT denoising iterations on the host cores"""
+
+    def __init__(self):
+        from oracle import ref_harness as rh         # allowed here: cpu_baseline / --impl reference legs only
+        from layoutdm_b200 import Vocab
+        from layoutdm_b200.synthetic import random_state_dict
+        self.sd = random_state_dict(Vocab.for_dataset("rico25"), num_timesteps=T, seed=0)
+        self.rh = rh
+        if rh.reference_available():
+            self.kind = "reference"
+            self.model, _ = rh.build_reference("rico25", T=T, state_dict=self.sd)
+            self.cfg = rh.sampling_cfg("random", num_timesteps=REF_NT)
+            self.what = "unmodified reference LayoutDM.sample (fp32 PyTorch eager, CPU)"
+        else:
+            from oracle import layoutdm_oracle as O
+            self.kind = "port"
+            self.O = O
+            self.orc = O.Oracle(O.RICO25, O.ModelSpec(T=T), self.sd)
+            self.what = "fp32 torch-CPU port of the reference path (oracle)"
+
+    def step(self, seed):
+        torch.manual_seed(seed)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            if self.kind == "reference":
+                out = self.model.sample(batch_size=REF_B, cond=None, sampling_cfg=self.cfg)
+                assert out["bbox"].shape[0] == REF_B
+            else:
+                O, vo = self.O, self.orc.vocab
+                x = torch.full((REF_B, vo.S), vo.mask_id, dtype=torch.long)
+                for i, (tm, tp) in enumerate(O.timestep_plan(T, REF_NT)):
+                    lp, _ = self.orc.step_logprob(x, tm, tp)
+                    x = O.draw(lp, O.SamplingCfg(name="random"), O.uniforms(seed, i, 0, 0, REF_B, vo.S, vo.C))
+        return time.perf_counter() - t0
+
+    def layouts_per_s(self, dt):
+        return REF_B / (dt * T / REF_NT)             # per-iteration cost does not depend on t: scale to the full T-step loop
+
+    def sample_desc(self, dt):
+        return (f"{REF_B} layouts x {REF_NT} of {T} denoising iterations per step ({dt:.1f} s of CPU work), scaled x{T / REF_NT:.1f} to T={T}; {self.what}")
 
 
 def run_reference_arm(args, world, rank):
     if rank != 0:
         return
-    # torchrun exports OMP_NUM_THREADS=1 for its workers: the CPU arm uses every host core it can get
-    torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
-    orc, O = make_cpu_oracle()
-    cores = torch.get_num_threads()
-    total_budget = 150.0
-    per = max(2.0, min(20.0, total_budget / (args.steps + args.warmup)))
-    B_s, n_t, t1 = cpu_sample_plan(per, orc, O)
-    ts = [int(round(i * (T - 1) / max(1, n_t - 1))) for i in range(n_t)][::-1] if n_t > 1 else [50]
-    for _ in range(args.warmup):
-        cpu_pass(orc, O, B_s, ts, 1)
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        cpu_pass(orc, O, B_s, ts, 2 + k)
-    dt = (time.perf_counter() - t0) / args.steps
-    lps = B_s / (dt * T / len(ts))                    # layouts per second for the full T-step loop
-    sample = f"{B_s} layouts x {len(ts)} of {T} timesteps per step (fp32 torch-CPU port of the reference path), extrapolated x{T / len(ts):.1f} to T={T}"
-    line = {"impl": "reference", "metric": METRIC, "value": lps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    cores = physical_cores()
+    torch.set_num_threads(cores)                     # torchrun exports OMP_NUM_THREADS=1: use the physical cores (no SMT oversubscription)
+    arm = CpuArm()
+    for w in range(max(1, args.warmup)):
+        arm.step(w)
+    dts = [arm.step(100 + k) for k in range(args.steps)]
+    dt = sum(dts) / len(dts)
+    lps = arm.layouts_per_s(dt)
+    line = {"impl": "reference", "metric": METRIC, "value": lps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(1, args.warmup),
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "rico25 unconditional, T=100, random sampling, N=25 (S=125, C=155); CPU sample of the batch-1024 workload"},
-            "cpu_baseline": {"value": lps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": "rico25 unconditional, T=100, random sampling, N=25 (S=125, C=155); bounded CPU sample of the batch-1024 workload"},
+            "cpu_baseline": {"value": lps, "unit": UNIT, "cores": cores, "kind": arm.kind, "sample": arm.sample_desc(dt),
+                             "best_step_value": arm.layouts_per_s(min(dts)), "step_seconds": [round(x, 3) for x in dts]},
             "e2e": {"value": lps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_reference(B, dev):
+    """the north star's denominator: the unmodified reference `LayoutDM.sample` run eagerly (fp32) on the same GPU, full
+    T=100 loop, chunks of <= 512 layouts (Converter limit, layout_tokenizer.py:530), synchronize-bracketed like test.py:194-203"""
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        return None
+    from layoutdm_b200 import Vocab
+    from layoutdm_b200.synthetic import random_state_dict
+    model, _ = rh.build_reference("rico25", T=T, state_dict=random_state_dict(Vocab.for_dataset("rico25"), num_timesteps=T, seed=0))
+    model = model.to(dev)
+    cfg = rh.sampling_cfg("random", num_timesteps=T)
+    chunks = [min(512, B - i) for i in range(0, B, 512)]
+    with torch.no_grad():
+        model.sample(batch_size=min(64, B), cond=None, sampling_cfg=rh.sampling_cfg("random", num_timesteps=5))   # warm-up (cuBLAS handles, allocator)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for b in chunks:
+            model.sample(batch_size=b, cond=None, sampling_cfg=cfg)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+    del model
+    torch.cuda.empty_cache()
+    return {"value": B / dt, "unit": UNIT, "seconds": dt, "kind": "reference",
+            "what": f"unmodified reference LayoutDM.sample, fp32 PyTorch eager on the same GPU, batch {B} in chunks of <= 512, T={T}, one pass"}
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -265,15 +326,19 @@ def run_b200_arm(args, world, rank, local):
                 "path_tflops": value / world * T * FLOPS_PER_LAYOUT_STEP / 1e12,
                 "path_frac": value / world * T * FLOPS_PER_LAYOUT_STEP / 1e12 / peaks["sustained"]}
 
-    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores ----
-    cpu = None
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores; reference on the same GPU ----
+    cpu = gpu_eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        orc, O = make_cpu_oracle()
-        B_s, n_t, _ = cpu_sample_plan(15.0, orc, O)
-        ts = [int(round(i * (T - 1) / max(1, n_t - 1))) for i in range(n_t)][::-1] if n_t > 1 else [50]
-        dt = cpu_pass(orc, O, B_s, ts, 3)
-        cpu = {"value": B_s / (dt * T / len(ts)), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{B_s} layouts x {len(ts)} of {T} timesteps ({dt:.1f} s of CPU work), extrapolated to T={T}; fp32 torch-CPU port of the reference path"}
+        cores = physical_cores()
+        torch.set_num_threads(cores)
+        arm = CpuArm()
+        arm.step(0)
+        dts = [arm.step(1 + k) for k in range(2)]
+        dt = sum(dts) / len(dts)
+        cpu = {"value": arm.layouts_per_s(dt), "unit": UNIT, "cores": cores, "kind": arm.kind, "sample": arm.sample_desc(dt)}
+        gpu_eager = gpu_eager_reference(B, dev)
+        if gpu_eager:
+            gpu_eager["speedup_e2e"] = e2e["value"] / gpu_eager["value"]
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -283,7 +348,7 @@ def run_b200_arm(args, world, rank, local):
                            "global_batch": total, "parallelism": f"dp{world} (batch-sharded replicas, one all-gather of ids)" if world > 1 else "single GPU",
                            "l2": "per-step activation working set (1.9 GB at B=1024) >> 126 MB L2, no explicit flush needed",
                            "operands": f"{args.dtype} tensor-core operands, fp32 accumulate / LayerNorm / softmax / posterior"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager}
         print(json.dumps(line), flush=True)
 
 

@@ -152,6 +152,7 @@ struct LdmHandle {
   CUtensorMap t_x16, t_z16;                                                  // K tails of the A-resident operands (128 x 16 boxes)
   CUtensorMap b_qkv16, b_hid16, b_z16, b_x16, b_x32, b_y32, b_logits;  // epilogue 32 x 32 blocks
   std::vector<void*> owned;
+  std::vector<void*> staging;  // ldm_create: fp32 uploads that only feed the packing kernels, released once those have run
 };
 
 namespace {
@@ -168,6 +169,19 @@ int dev_upload(LdmHandle* h, T** p, const T* src, size_t n) {
   if (rc) return rc;
   CK(cudaMemcpy(*p, src, n * sizeof(T), cudaMemcpyHostToDevice));
   return LDM_OK;
+}
+
+// upload that only feeds a packing / table kernel of ldm_create: freed right after those kernels have run
+template <typename T>
+int dev_upload_tmp(LdmHandle* h, T** p, const T* src, size_t n) {
+  CK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  h->staging.push_back(*p);
+  CK(cudaMemcpy(*p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return LDM_OK;
+}
+void free_staging(LdmHandle* h) {
+  for (void* p : h->staging) cudaFree(p);
+  h->staging.clear();
 }
 
 int pack16(LdmHandle* h, void** dst, const float* src_dev, const int* row_map_dev, int dst_rows, int dst_cols, int src_cols,
@@ -244,12 +258,21 @@ int set_smem(K kernel, int bytes) {
   return LDM_OK;
 }
 
+void free_workspace(LdmHandle* h) {
+  void** ws[] = {&h->x16, &h->qkv16, &h->att16, &h->z16, &h->hid16, reinterpret_cast<void**>(&h->x32), reinterpret_cast<void**>(&h->y32),
+                 reinterpret_cast<void**>(&h->logits), reinterpret_cast<void**>(&h->ids[0]), reinterpret_cast<void**>(&h->ids[1]),
+                 reinterpret_cast<void**>(&h->ids_final), reinterpret_cast<void**>(&h->c_seq), reinterpret_cast<void**>(&h->c_seq_orig),
+                 reinterpret_cast<void**>(&h->c_mask), reinterpret_cast<void**>(&h->ln_stats)};
+  for (void** p : ws) { if (*p) cudaFree(*p); *p = nullptr; }
+  h->cap = 0;
+}
+
 int ensure_workspace(LdmHandle* h, int n_layouts) {
   n_layouts = (n_layouts + 1) & ~1;     // GEMM CTA pairs work on 256-row blocks: keep an even number of layout tiles
   if (n_layouts <= h->cap) return LDM_OK;
-  // free the old workspace
-  void* olds[] = {h->x16, h->qkv16, h->att16, h->z16, h->hid16, h->x32, h->y32, h->logits, h->ids[0], h->ids[1], h->ids_final, h->c_seq, h->c_seq_orig, h->c_mask, h->ln_stats};
-  for (void* p : olds) if (p) cudaFree(p);
+  // free the old workspace: nothing may still be running on it, and a failed reallocation must not leave stale pointers behind
+  CK(cudaDeviceSynchronize());
+  free_workspace(h);
   const size_t M = static_cast<size_t>(n_layouts) * kBM;
   const int d = h->desc.d_model, ff = h->desc.d_ff;
   CK(cudaMalloc(&h->x16, M * d * 2));
@@ -479,9 +502,9 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   // AdaLN (scale, shift) for every (layer, t)
   {
     float *emb = nullptr, *lw = nullptr, *lb = nullptr;
-    TRY(dev_upload(h, &emb, w->norm1_emb, static_cast<size_t>(L) * T * d));
-    TRY(dev_upload(h, &lw, w->norm1_w, static_cast<size_t>(L) * 2 * d * d));
-    TRY(dev_upload(h, &lb, w->norm1_b, static_cast<size_t>(L) * 2 * d));
+    TRY(dev_upload_tmp(h, &emb, w->norm1_emb, static_cast<size_t>(L) * T * d));
+    TRY(dev_upload_tmp(h, &lw, w->norm1_w, static_cast<size_t>(L) * 2 * d * d));
+    TRY(dev_upload_tmp(h, &lb, w->norm1_b, static_cast<size_t>(L) * 2 * d));
     TRY(dev_alloc(h, &h->adaln, static_cast<size_t>(L) * T * 2 * d));
     adaln_table_kernel<<<dim3(T, L), 256, d * sizeof(float)>>>(emb, lw, lb, h->adaln, T, d);
     if (cudaGetLastError() != cudaSuccess) { ldm_destroy(h); return fail(LDM_ERR_CUDA, "adaln_table_kernel launch failed"); }
@@ -503,20 +526,20 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
 
   for (int l = 0; l < L; ++l) {
     float* tmp = nullptr;
-    TRY(dev_upload(h, &tmp, w->in_proj_w + static_cast<size_t>(l) * 3 * d * d, static_cast<size_t>(3) * d * d));
+    TRY(dev_upload_tmp(h, &tmp, w->in_proj_w + static_cast<size_t>(l) * 3 * d * d, static_cast<size_t>(3) * d * d));
     TRY(pack16(h, &h->wqkv[l], tmp, qmap_dev, kQkvN, d, d));
     std::vector<float> bq(kQkvN, 0.0f);
     for (int r = 0; r < kQkvN; ++r) if (qmap[r] >= 0) bq[r] = w->in_proj_b[static_cast<size_t>(l) * 3 * d + qmap[r]];
     // column dh of every V head = 1 (zero weight row + unit bias): the attention kernel reads the softmax denominator from it
     for (int hh = 0; hh < desc->n_heads; ++hh) bq[2 * 8 * kHeadPad + hh * kHeadPad + dh] = 1.0f;
     TRY(dev_upload(h, &h->bqkv[l], bq.data(), bq.size()));
-    TRY(dev_upload(h, &tmp, w->out_proj_w + static_cast<size_t>(l) * d * d, static_cast<size_t>(d) * d));
+    TRY(dev_upload_tmp(h, &tmp, w->out_proj_w + static_cast<size_t>(l) * d * d, static_cast<size_t>(d) * d));
     TRY(pack16(h, &h->wo[l], tmp, nullptr, d, kAttN, d, amap_dev));      // K = 512: head h occupies columns h*64 .. h*64+57
     TRY(dev_upload(h, &h->bo[l], w->out_proj_b + static_cast<size_t>(l) * d, static_cast<size_t>(d)));
-    TRY(dev_upload(h, &tmp, w->linear1_w + static_cast<size_t>(l) * ff * d, static_cast<size_t>(ff) * d));
+    TRY(dev_upload_tmp(h, &tmp, w->linear1_w + static_cast<size_t>(l) * ff * d, static_cast<size_t>(ff) * d));
     TRY(pack16(h, &h->w1[l], tmp, nullptr, ff, d, d));
     TRY(dev_upload(h, &h->b1[l], w->linear1_b + static_cast<size_t>(l) * ff, static_cast<size_t>(ff)));
-    TRY(dev_upload(h, &tmp, w->linear2_w + static_cast<size_t>(l) * d * ff, static_cast<size_t>(d) * ff));
+    TRY(dev_upload_tmp(h, &tmp, w->linear2_w + static_cast<size_t>(l) * d * ff, static_cast<size_t>(d) * ff));
     TRY(pack16(h, &h->w2[l], tmp, nullptr, d, ff, ff));
     TRY(dev_upload(h, &h->b2[l], w->linear2_b + static_cast<size_t>(l) * d, static_cast<size_t>(d)));
     TRY(dev_upload(h, &h->ln2w[l], w->norm2_w + static_cast<size_t>(l) * d, static_cast<size_t>(d)));
@@ -528,7 +551,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   }
   {
     float* tmp = nullptr;
-    TRY(dev_upload(h, &tmp, w->head_w, static_cast<size_t>(C) * d));
+    TRY(dev_upload_tmp(h, &tmp, w->head_w, static_cast<size_t>(C) * d));
     std::vector<int> hmap(kLogitLd);
     for (int r = 0; r < kLogitLd; ++r) hmap[r] = r < C ? r : -1;
     int* hmap_dev = nullptr;
@@ -548,6 +571,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
     if (cudaGetLastError() != cudaSuccess) { ldm_destroy(h); return fail(LDM_ERR_CUDA, "lae_table_kernel launch failed"); }
   }
   if (cudaDeviceSynchronize() != cudaSuccess) { ldm_destroy(h); return fail(LDM_ERR_CUDA, "weight packing failed: %s", cudaGetErrorString(cudaGetLastError())); }
+  free_staging(h);
 
   if (h->bf16) {
     TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, true, true>, GemmSmem<256, 5, EPI_QKV, true>::kBytes)));
@@ -572,9 +596,11 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
 int ldm_destroy(LdmHandle* h) {
   if (!h) return LDM_OK;
   cudaSetDevice(h->desc.device);
+  cudaDeviceSynchronize();
   for (void* p : h->owned) cudaFree(p);
-  void* ws[] = {h->x16, h->qkv16, h->att16, h->z16, h->hid16, h->x32, h->y32, h->logits, h->ids[0], h->ids[1], h->ids_final, h->c_seq, h->c_seq_orig, h->c_mask, h->c_tbl};
-  for (void* p : ws) if (p) cudaFree(p);
+  free_staging(h);
+  free_workspace(h);
+  if (h->c_tbl) cudaFree(h->c_tbl);
   delete h;
   return LDM_OK;
 }

@@ -38,10 +38,11 @@ def index_to_log_onehot(x: torch.Tensor, num_classes: int) -> torch.Tensor:
 
 
 def duplicate_cond(cond: Dict, batch_size: int) -> Dict:
-    """helpers/task.py:235-248"""
+    """helpers/task.py:235-248: one condition, many outputs.  Per-layout tensors are repeated along dim 0; the (C, C)
+    refinement band table is shared by all layouts and stays as it is."""
     if cond["seq"].size(0) == 1 and batch_size > 1:
         for k in cond:
-            if isinstance(cond[k], torch.Tensor):
+            if isinstance(cond[k], torch.Tensor) and k != "refine_table":
                 cond[k] = cond[k].repeat([batch_size] + [1] * (cond[k].dim() - 1))
     return cond
 
@@ -60,8 +61,9 @@ class FusedMaskAndReplaceDiffusion:
             bbox_centers = [bt.clustering_models[f"{k}-{self.vocab.n_bins}"].cluster_centers_.reshape(-1) for k in ("x", "y", "w", "h")]
         self.bbox_centers = bbox_centers if bbox_centers is not None else linear_centers(self.vocab.n_bins)
         self._step_ctr = 0
-        self._seed = 0
-        self.logit_adjust_fn = None      # optional hook f(t, cond, model_log_prob (B,C,S), sampling_cfg) for cond=relation
+        self._seed: Optional[int] = None     # noise key of `_sample_single_step` trajectories (None: drawn from torch's generator)
+        self._last_t: Optional[int] = None
+        self.logit_adjust_fn = None      # optional hook f(t: int, cond, model_log_prob (B,C,S), sampling_cfg) for cond=relation
 
     @property
     def device(self) -> torch.device:
@@ -120,9 +122,12 @@ class FusedMaskAndReplaceDiffusion:
 
     def _step_ids(self, ids, t_model, t_post, sampling_cfg, cond, seed, step_ctr, b_global0=0):
         if cond is not None and cond.get("type") == "relation" and self.logit_adjust_fn is not None:
-            _, _, lp = self.engine.step(ids, t_model, t_post, sampling_cfg, cond, seed, step_ctr, b_global0, want_logprob=True)
-            lp = self.logit_adjust_fn(t_model, cond, lp.permute(0, 2, 1).contiguous(), sampling_cfg)      # (B,C,S) like the reference
-            # pad-disable is applied after `update` in the reference (base.py:261-284)
+            # base.py:243-284 order: strong mask -> update() -> PAD-disable -> draw.  The first call returns the log-probs with the
+            # strong mask only (PAD-disable off: `update` must see what the reference's sees), the hook edits them, PAD-disable
+            # is applied here, the second call draws from the result.  `t` is an int like in the reference (base.py:262).
+            pre = dict(cond); pre["_pad_disable"] = False
+            _, _, lp = self.engine.step(ids, t_model, t_post, sampling_cfg, pre, seed, step_ctr, b_global0, want_logprob=True)
+            lp = self.logit_adjust_fn(int(t_model), cond, lp.permute(0, 2, 1).contiguous(), sampling_cfg)      # (B,C,S) like the reference
             lp = lp.permute(0, 2, 1).contiguous()
             S = ids.shape[1]
             pad_mask = (torch.arange(S, device=ids.device)[None] % self.vocab.n_attr != 0) & (cond["seq"] != self.vocab.pad_id)
@@ -148,6 +153,11 @@ class FusedMaskAndReplaceDiffusion:
             cond_d = {k: (v.to(self.device) if isinstance(v, torch.Tensor) else v) for k, v in cond.items()}
             if cond_d.get("type") == "refinement" and "refine_table" not in cond_d:
                 cond_d = self._prepare_cond(cond_d, ids.shape[0], sampling_cfg)
+        # noise key: like the reference, the draws come from torch's global generator -- a new key is derived from it at the start
+        # of every trajectory (timesteps strictly decrease inside one), unless reset_noise(seed) pinned one
+        if self._seed is None or (self._last_t is not None and t_model >= self._last_t and not self._pinned):
+            self._seed, self._step_ctr = self._new_seed(), 0
+        self._last_t = t_model
         out = self._step_ids(ids, t_model, t_post, sampling_cfg, cond_d, self._seed, self._step_ctr)
         self._step_ctr += 1
         return index_to_log_onehot(out, self.num_classes)
@@ -156,8 +166,11 @@ class FusedMaskAndReplaceDiffusion:
         """corruption x_t ~ q(x_t | x_0) on ids (constrained.py:223-230 applied per attribute as in :232-260)"""
         return self.engine.q_sample(x0, t, self._new_seed() if seed is None else seed)
 
-    def reset_noise(self, seed: int):
-        self._seed, self._step_ctr = seed, 0
+    _pinned = False
+
+    def reset_noise(self, seed: Optional[int] = None):
+        """pin the noise key of the following `_sample_single_step` calls (seed=None: back to torch's global generator)"""
+        self._seed, self._step_ctr, self._last_t, self._pinned = seed, 0, None, seed is not None
 
     def predict_logits(self, ids: torch.Tensor, t: int) -> torch.Tensor:
         """CategoricalTransformer.forward (nn_lib.py:191-237): ids (B,S) -> logits (B,S,C) on the GPU"""
@@ -234,17 +247,14 @@ def patch_reference_model(model, operand_dtype: str = "fp16", device=None):
     eng = Engine.from_state_dict(model.state_dict(), vocab, num_timesteps=core.num_timesteps, q_type=q_type,
                                  operand_dtype=operand_dtype, device=device)
     fused = FusedMaskAndReplaceDiffusion(eng, tok)
-    if q_type == "constrained" or True:
-        try:
-            from trainer.models.categorical_diffusion.logit_adjustment import update as _update
+    # cond=relation: the reference's own gradient update (logit_adjustment.py:88-126) runs between the posterior and the draw.
+    # `model` is a live reference object, so its package is importable; an import failure is an error, not a silent downgrade.
+    import importlib
+    _update = importlib.import_module(type(core).__module__.rsplit(".", 1)[0] + ".logit_adjustment").update
 
-            def _hook(t, cond, model_log_prob, sampling_cfg):
-                if "batch_w_canvas" not in cond:
-                    return model_log_prob
-                return _update(t=t, cond=cond, model_log_prob=model_log_prob, tokenizer=tok, sampling_cfg=sampling_cfg)
-            fused.logit_adjust_fn = _hook
-        except Exception:       # reference not importable: relation conditioning falls back to plain sampling
-            pass
+    def _hook(t, cond, model_log_prob, sampling_cfg):
+        return _update(t=t, cond=cond, model_log_prob=model_log_prob, tokenizer=tok, sampling_cfg=sampling_cfg)
+    fused.logit_adjust_fn = _hook
     core.sample = fused.sample
     core._sample_single_step = fused._sample_single_step
     core._ldm_b200 = fused

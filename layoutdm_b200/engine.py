@@ -150,9 +150,11 @@ class Engine:
         if cond.get("seq_orig") is not None and cond.get("refine_table") is not None:
             so = cond["seq_orig"].to(self.device, torch.int64).contiguous(); keep.append(so)
             tb = cond["refine_table"].to(self.device, torch.float32).contiguous(); keep.append(tb)
-            assert tb.shape == (self.vocab.C, self.vocab.C)
+            assert tb.shape == (self.vocab.C, self.vocab.C), f"refine_table must be (C, C) = ({self.vocab.C}, {self.vocab.C}), got {tuple(tb.shape)}"
             c.seq_orig, c.refine_table = so.data_ptr(), tb.data_ptr()
         c.pad_disable = 1 if cond.get("type") in ("c", "cwh", "refinement", "relation") else 0   # base.py:272
+        if cond.get("_pad_disable") is not None:                     # relation hook: PAD-disable comes after update() (base.py:261-284)
+            c.pad_disable = 1 if cond["_pad_disable"] else 0
         return c, keep
 
     def step(self, ids_in: torch.Tensor, t_model: int, t_post: int, sampling, cond: Optional[dict] = None, seed: int = 0,
@@ -265,6 +267,7 @@ class Engine:
             if cond.get("seq_orig") is not None and cond.get("refine_table") is not None:
                 so = cond["seq_orig"].to(torch.int64).contiguous()
                 tb = cond["refine_table"].to(torch.float32).contiguous()
+                assert tb.shape == (self.vocab.C, self.vocab.C), f"refine_table must be (C, C), got {tuple(tb.shape)}"
             pad_disable = 1 if cond.get("type") in ("c", "cwh", "refinement", "relation") else 0
             for t in (seq, mask, so, tb):
                 assert t is None or not t.is_cuda

@@ -7,7 +7,7 @@ reference's `LayoutDM.sample()` path.  Only `tests/`, `__graft_entry__.smoke()` 
 fails loudly when its CUDA library is missing.
 
 Parity pin: the reference has NO tests / golden vectors of its own.  This restatement is
-pinned against the *unmodified reference itself*, imported through `tests/_shims` in the build container
+pinned against the *unmodified reference itself*, imported through `oracle/ref_shims` in the build container
 (`tests/golden/make_golden.py`, `tests/test_oracle_vs_reference.py`), and against the fixtures that script
 commits under `tests/golden/` (those travel to the GPU box, /root/reference does not).
 

@@ -1,6 +1,6 @@
 """
 Generates the committed golden fixtures under tests/golden/*.npz by running the UNMODIFIED reference
-(/root/reference, imported through tests/_shims) on CPU, and checks the oracle restatement against it while
+(/root/reference, imported through oracle/ref_shims) on CPU, and checks the oracle restatement against it while
 doing so.  Run in the build container only:
 
     python tests/golden/make_golden.py
