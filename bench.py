@@ -133,8 +133,9 @@ def max_over_ranks(x: float, world, device):
 # oracle/make_ref.py packaged (oracle/_ref/trainer_ref.zip; /root/reference does not exist on the GPU box), on the host
 # cores.  Falls back to the oracle port (kind "port") only if the archive is missing.
 # --------------------------------------------------------------------------------------------------------------
-REF_B, REF_NT = 64, 8        # fixed bounded sample: 64 layouts x 8 of the T=100 denoising iterations per step (B=64 is the
-                             # reference's most efficient CPU batch per layout: measured 64x8 / 256x2 / 512x1 -> 1.96 / 1.28 / 1.12 layouts/s on 8 cores)
+REF_B, REF_NT = 64, 100      # fixed bounded sample: one step = sample() of 64 layouts through the FULL T=100 loop (no extrapolation in T;
+                             # B=64 is the reference's most efficient CPU batch per layout: measured 64 / 256 / 512 -> 1.96 / 1.28 / 1.12
+                             # layouts/s on 8 cores).  ~3.6 s per step on the 64 physical cores of the GPU box (r02b: 17.7 layouts/s)
 
 
 def physical_cores(cap=64):
@@ -200,7 +201,8 @@ class CpuArm:
         return REF_B / (dt * T / REF_NT)             # per-iteration cost does not depend on t: scale to the full T-step loop
 
     def sample_desc(self, dt):
-        return (f"{REF_B} layouts x {REF_NT} of {T} denoising iterations per step ({dt:.1f} s of CPU work), scaled x{T / REF_NT:.1f} to T={T}; {self.what}")
+        scaled = "" if REF_NT == T else f", scaled x{T / REF_NT:.1f} to T={T}"
+        return f"{REF_B} layouts x {REF_NT} of {T} denoising iterations per step ({dt:.1f} s of CPU work per step){scaled}; {self.what}"
 
 
 def run_reference_arm(args, world, rank):
@@ -333,9 +335,9 @@ def run_b200_arm(args, world, rank, local):
         torch.set_num_threads(cores)
         arm = CpuArm()
         arm.step(0)
-        dts = [arm.step(1 + k) for k in range(2)]
+        dts = [arm.step(1 + k) for k in range(3)]                 # ~15 s of CPU work in total
         dt = sum(dts) / len(dts)
-        cpu = {"value": arm.layouts_per_s(dt), "unit": UNIT, "cores": cores, "kind": arm.kind, "sample": arm.sample_desc(dt)}
+        cpu = {"value": arm.layouts_per_s(dt), "unit": UNIT, "cores": cores, "kind": arm.kind, "sample": arm.sample_desc(dt) + f"; mean of {len(dts)} steps after 1 warm-up"}
         gpu_eager = gpu_eager_reference(B, dev)
         if gpu_eager:
             gpu_eager["speedup_e2e"] = e2e["value"] / gpu_eager["value"]

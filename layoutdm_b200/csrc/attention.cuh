@@ -80,6 +80,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  pdl_sync();
 
   if (warp == 0) {
     // ===================== producer: loads two items ahead, stores O (whole warp loops, one elected lane issues) =====================

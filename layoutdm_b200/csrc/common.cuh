@@ -29,6 +29,16 @@ LDM_DEVINL bool elect_one() {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// programmatic dependent launch (every kernel of the step is launched with programmatic stream serialization): the
+// prologue (barrier init, TMEM allocation, descriptor prefetch, parameter loads from constant tables) runs while the
+// previous kernel drains; pdl_wait() returns once the previous grid has completed and its writes are visible.  No global
+// access that depends on (or could overwrite the inputs of) the previous kernel may precede it.
+// ------------------------------------------------------------------------------------------------------------
+LDM_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+LDM_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+LDM_DEVINL void pdl_sync() { pdl_wait(); pdl_launch_dependents(); }
+
+// ------------------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------------------
 LDM_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {

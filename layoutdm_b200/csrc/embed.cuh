@@ -51,6 +51,7 @@ embed_adaln_kernel(const long long* __restrict__ ids /*[B][S]*/, const float* __
   typename O::T* x16 = static_cast<typename O::T*>(x16_);
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp_global >= n_layouts_padded * 128) return;
+  pdl_sync();                                // ids come from the previous step's draw; x32 / x16 may still be read by it
   const int b = warp_global >> 7, s = warp_global & 127;
   const size_t row = static_cast<size_t>(warp_global);
   const int nv = d / 4;                      // float4 per row (464 / 4 = 116)

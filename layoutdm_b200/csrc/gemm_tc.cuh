@@ -175,6 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   cluster_sync_all();                                        // both CTAs' barriers and TMEM are ready
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_sync();                                                // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================

@@ -130,6 +130,7 @@ struct LdmHandle {
   int64_t launches = 0;
   int gemm_dbg = 0;           // env LDM_GEMM_DEBUG (bring-up probe, see GemmParams::dbg)
   int debug_generic_posterior = 0;   // env LDM_GENERIC_POSTERIOR=1: always take the all-classes posterior / sampling kernel (tests)
+  int pdl = 1;                // env LDM_PDL=0: no programmatic dependent launch (LN GEMMs launched cooperatively instead)
   int debug_stop_after = 0;   // test tap: stop the denoiser after this many launches (0 = run everything)
   bool prof = false;          // per-kernel CUDA-event timing (ldm_profile_begin/end)
   struct ProfRec { int cat; cudaEvent_t a, b; };
@@ -240,15 +241,22 @@ struct ProfScope {   // counts the launch; when profiling is on, brackets it wit
   ~ProfScope() { if (b) cudaEventRecord(b, st); }
 };
 
-// Cooperative launch: every CTA of the grid is guaranteed to be resident at the same time (or the launch fails).  The LN GEMMs
-// need it: neighbouring CTA pairs exchange row statistics while both are running (gemm_tc.cuh).
+// Launch of one kernel of the step.  Default: programmatic dependent launch (cudaLaunchAttributeProgrammaticStreamSerialization):
+// the kernel's CTAs may start while the previous kernel of the stream drains; every kernel calls pdl_sync() (griddepcontrol.wait
+// + launch_dependents) after its prologue and before its first dependent global access, so barrier init / TMEM allocation /
+// descriptor prefetch / parameter loads overlap the predecessor's tail and the launch latency disappears.
+// The LN GEMMs exchange row statistics between neighbouring CTA pairs while both run, i.e. all their CTAs must be resident
+// together.  With PDL that holds by construction: the grid has at most one CTA per SM (checked at create), its predecessor
+// never waits on it, and its successor cannot start before every CTA of it has passed pdl_sync().  With LDM_PDL=0 the LN GEMMs
+// are launched cooperatively instead (the runtime then guarantees co-residency or fails the launch).
 template <typename... KArgs, typename... Args>
-cudaError_t launch_cooperative(void (*kernel)(KArgs...), int grid, int block, int smem, cudaStream_t st, Args&&... args) {
+cudaError_t launch_step(const LdmHandle* h, void (*kernel)(KArgs...), int grid, int block, int smem, cudaStream_t st, bool coresident, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  cfg.attrs = at; cfg.numAttrs = 0;
+  if (h->pdl) { at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1; cfg.numAttrs = 1; }
+  else if (coresident) { at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1; cfg.numAttrs = 1; }
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -335,8 +343,8 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
   {
     const int warps = np * 128, blocks = (warps * 32 + 255) / 256;
     ProfScope ps(h, CAT_EMBED, st);
-    embed_adaln_kernel<BF16><<<blocks, 256, 0, st>>>(ids_in, h->cat_emb, h->pos, h->adaln + (static_cast<size_t>(0) * T + t_model) * 2 * d,
-                                                     h->x32, h->x16, n, np, h->S, d);
+    CK(launch_step(h, embed_adaln_kernel<BF16>, blocks, 256, 0, st, false, ids_in, (const float*)h->cat_emb, (const float*)h->pos,
+                   (const float*)(h->adaln + (static_cast<size_t>(0) * T + t_model) * 2 * d), h->x32, h->x16, n, np, h->S, d));
   }
   LDM_STAGE_DONE();
   for (int l = 0; l < L; ++l) {
@@ -344,30 +352,30 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       GemmParams p{M, kQkvN, d, kQkvN / 256, h->bqkv[l], h->qkv16, kQkvN, 1.0f / sqrtf(static_cast<float>(d / h->desc.n_heads)), 8 * kHeadPad};
       p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles);
       ProfScope ps(h, CAT_QKV, st);
-      gemm_tc_kernel<256, 256, 5, EPI_QKV, BF16, true><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 5, EPI_QKV, true>::kBytes, st>>>(
-          h->m_x16, h->m_wqkv[l], h->b_qkv16, h->b_qkv16, h->b_qkv16, h->t_x16, p);
+      CK(launch_step(h, gemm_tc_kernel<256, 256, 5, EPI_QKV, BF16, true>, pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 5, EPI_QKV, true>::kBytes, st, false,
+                     h->m_x16, h->m_wqkv[l], h->b_qkv16, h->b_qkv16, h->b_qkv16, h->t_x16, p));
     }
     LDM_STAGE_DONE();
     {
       ProfScope ps(h, CAT_ATTN, st);
-      attention_kernel<BF16><<<std::min(np * h->desc.n_heads, 2 * h->num_sms), kAttThreads, kAttSmemBytes, st>>>(h->m_qkv16, h->m_att16, h->S, h->desc.n_heads, np,
-                                                                                                                     d / h->desc.n_heads);
+      CK(launch_step(h, attention_kernel<BF16>, std::min(np * h->desc.n_heads, 2 * h->num_sms), kAttThreads, kAttSmemBytes, st, false,
+                     h->m_qkv16, h->m_att16, h->S, h->desc.n_heads, np, d / h->desc.n_heads));
     }
     LDM_STAGE_DONE();
     {  // out-projection + bias + residual (from the NORMALISED x) -> y32 ; z16 = LayerNorm2(y)   [fused epilogue]
       GemmParams p{M, d, kAttN, 2, h->bo[l], h->z16, d, 1.0f, 0, h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr};
       p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch;
       ProfScope ps(h, CAT_OUTPROJ, st);
-      CK(launch_cooperative(gemm_tc_kernel<224, 240, 3, EPI_LN, BF16>, ln_grid, kGemmThreads, GemmSmem<240, 3, EPI_LN>::kBytes, st,
-                            h->m_att16, h->m_wo[l], h->b_z16, h->b_x32, h->b_y32, h->b_y32, p));
+      CK(launch_step(h, gemm_tc_kernel<224, 240, 3, EPI_LN, BF16>, ln_grid, kGemmThreads, GemmSmem<240, 3, EPI_LN>::kBytes, st, true,
+                     h->m_att16, h->m_wo[l], h->b_z16, h->b_x32, h->b_y32, h->b_y32, p));
     }
     LDM_STAGE_DONE();
     {  // FF1 + ReLU
       GemmParams p{M, ff, d, (ff + 255) / 256, h->b1[l], h->hid16, ff, 1.0f, 0};   // 7 tiles of 256 columns + one of 64
       p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles);
       ProfScope ps(h, CAT_FF1, st);
-      gemm_tc_kernel<256, 256, 5, EPI_RELU, BF16, true><<<pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 5, EPI_RELU, true>::kBytes, st>>>(
-          h->m_z16, h->m_w1[l], h->b_hid16, h->b_hid16, h->b_hid16, h->t_z16, p);
+      CK(launch_step(h, gemm_tc_kernel<256, 256, 5, EPI_RELU, BF16, true>, pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 5, EPI_RELU, true>::kBytes, st, false,
+                     h->m_z16, h->m_w1[l], h->b_hid16, h->b_hid16, h->b_hid16, h->t_z16, p));
     }
     LDM_STAGE_DONE();
     {  // FF2 + bias + residual ; next block's AdaLN(h, t) (fp32 residual + 16-bit operand) or the head LayerNorm   [fused epilogue]
@@ -381,16 +389,16 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       }
       p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch;
       ProfScope ps(h, CAT_FF2, st);
-      CK(launch_cooperative(gemm_tc_kernel<224, 240, 5, EPI_LN, BF16>, ln_grid, kGemmThreads, GemmSmem<240, 5, EPI_LN>::kBytes, st,
-                            h->m_hid16, h->m_w2[l], *mo, h->b_y32, h->b_x32, h->b_x32, p));
+      CK(launch_step(h, gemm_tc_kernel<224, 240, 5, EPI_LN, BF16>, ln_grid, kGemmThreads, GemmSmem<240, 5, EPI_LN>::kBytes, st, true,
+                     h->m_hid16, h->m_w2[l], *mo, h->b_y32, h->b_x32, h->b_x32, p));
     }
     LDM_STAGE_DONE();
   }
   {  // vocabulary head -> fp32 logits
     GemmParams p{M, kLogitLd, d, 1, nullptr, h->logits, kLogitLd, 1.0f, 0};
     ProfScope ps(h, CAT_HEAD, st);
-    gemm_tc_kernel<160, 160, 5, EPI_F32, BF16><<<pair_grid(1), kGemmThreads, GemmSmem<160, 5, EPI_F32>::kBytes, st>>>(
-        h->m_z16, h->m_whead, h->b_logits, h->b_logits, h->b_logits, h->b_logits, p);
+    CK(launch_step(h, gemm_tc_kernel<160, 160, 5, EPI_F32, BF16>, pair_grid(1), kGemmThreads, GemmSmem<160, 5, EPI_F32>::kBytes, st, false,
+                   h->m_z16, h->m_whead, h->b_logits, h->b_logits, h->b_logits, h->b_logits, p));
   }
 #undef LDM_STAGE_DONE
   CK(cudaGetLastError());
@@ -454,8 +462,8 @@ int step_impl(LdmHandle* h, int B, const long long* ids_in, int t_model, int t_p
                       (p.mode == SAMP_DETERMINISTIC || p.mode == SAMP_RANDOM || p.mode == SAMP_GUMBEL ||
                        (p.mode == SAMP_TOP_P && p.top_p < 0.9999f)) && !h->debug_generic_posterior;
     for (int g = 0; g < p.n_attr; ++g) group_path = group_path && p.grp_n[g] <= 32;
-    if (group_path) posterior_sample_group_kernel<<<blocks, 256, 0, st>>>(p);
-    else posterior_sample_kernel<<<blocks, 256, 0, st>>>(p);
+    if (group_path) CK(launch_step(h, posterior_sample_group_kernel, blocks, 256, 0, st, false, p));
+    else CK(launch_step(h, posterior_sample_kernel, blocks, 256, 0, st, false, p));
   }
   CK(cudaGetLastError());
   return LDM_OK;
@@ -492,6 +500,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   h->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("LDM_GEMM_DEBUG")) h->gemm_dbg = atoi(e);
   if (const char* e = getenv("LDM_GENERIC_POSTERIOR")) h->debug_generic_posterior = atoi(e);
+  if (const char* e = getenv("LDM_PDL")) h->pdl = atoi(e);
 #define TRY(x) do { rc = (x); if (rc) { ldm_destroy(h); return rc; } } while (0)
 
   TRY(dev_upload(h, &h->cat_emb, w->cat_emb, static_cast<size_t>(C) * d));

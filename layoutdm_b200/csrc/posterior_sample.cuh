@@ -277,6 +277,7 @@ LDM_DEVINL void posterior_token_generic(const StepParams& p, const int token, co
 __global__ void __launch_bounds__(256) posterior_sample_kernel(const StepParams p) {
   const int token = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (token >= p.n_layouts * p.S) return;
+  pdl_sync();
   posterior_token_generic(p, token, lane);
 }
 
@@ -290,6 +291,7 @@ __global__ void __launch_bounds__(256) posterior_sample_kernel(const StepParams 
 __global__ void __launch_bounds__(256) posterior_sample_group_kernel(const StepParams p) {
   const int token = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (token >= p.n_layouts * p.S) return;
+  pdl_sync();
   const int b = token / p.S, s = token % p.S;
   const int C = p.C;
   const int x_t = static_cast<int>(p.ids_in[token]);
