@@ -597,6 +597,19 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
     TRY((set_smem(gemm_tc_kernel<224, 240, 3, EPI_LN, false>, GemmSmem<240, 3, EPI_LN>::kBytes)));
     TRY((set_smem(attention_kernel<false>, kAttSmemBytes)));
   }
+  if (h->pdl) {
+    // PDL replaces the cooperative launch of the LN GEMMs (see launch_step): their co-residency argument needs one CTA pair per
+    // SM pair to fit at once.  Ask the runtime; otherwise fall back to cooperative launches.
+    auto fits = [&](auto kernel, int smem) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(h->num_sms & ~3); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = smem;
+      int n = 0;
+      return cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) == cudaSuccess && 2 * n >= (h->num_sms & ~3);
+    };
+    const bool ok = h->bf16 ? (fits(gemm_tc_kernel<224, 240, 5, EPI_LN, true>, GemmSmem<240, 5, EPI_LN>::kBytes) && fits(gemm_tc_kernel<224, 240, 3, EPI_LN, true>, GemmSmem<240, 3, EPI_LN>::kBytes))
+                            : (fits(gemm_tc_kernel<224, 240, 5, EPI_LN, false>, GemmSmem<240, 5, EPI_LN>::kBytes) && fits(gemm_tc_kernel<224, 240, 3, EPI_LN, false>, GemmSmem<240, 3, EPI_LN>::kBytes));
+    if (!ok) { cudaGetLastError(); h->pdl = 0; }
+  }
 #undef TRY
   *out = h;
   return LDM_OK;

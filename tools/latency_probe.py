@@ -17,4 +17,4 @@ for B, T_eval in ((1, 100), (8, 50), (8, 100), (64, 100), (256, 100)):
     for i in range(n): eng.sample_loop(B, plan, cfg, seed=2 + i)
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / n
     out[f"B{B}_T{T_eval}"] = {"ms_per_call": round(dt * 1e3, 2), "us_per_step": round(dt * 1e6 / T_eval, 1), "layouts_per_s": round(B / dt, 1)}
-print(json.dumps({"graph": os.environ.get("LDM_GRAPH", "0"), **out}))
+print(json.dumps({"pdl": os.environ.get("LDM_PDL", "1"), "graph": os.environ.get("LDM_GRAPH", "1"), **out}))
