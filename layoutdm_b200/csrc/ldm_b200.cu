@@ -153,6 +153,15 @@ struct LdmHandle {
   CUtensorMap t_x16, t_z16;                                                  // K tails of the A-resident operands (128 x 16 boxes)
   CUtensorMap b_qkv16, b_hid16, b_z16, b_x16, b_x32, b_y32, b_logits;  // epilogue 32 x 32 blocks
   std::vector<void*> owned;
+  // CUDA graph of the whole T-step loop (ldm_sample_loop): captured once per (batch, plan, sampling, conditioning kind) and
+  // replayed; everything that changes from call to call lives in device memory (noise key block, staged cond / start ids)
+  int use_graph = 1;           // env LDM_GRAPH=0: plain stream launches
+  cudaStream_t cap_stream = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  uint64_t graph_key = 0;
+  unsigned long long* call_block = nullptr;   // device {seed, b_global0}
+  uint64_t ws_generation = 0;  // bumped when the workspace is reallocated (captured pointers die)
+  int64_t graph_launches = 0;  // kernel launches inside the captured graph
   std::vector<void*> staging;  // ldm_create: fp32 uploads that only feed the packing kernels, released once those have run
 };
 
@@ -307,6 +316,7 @@ int ensure_workspace(LdmHandle* h, int n_layouts) {
   CK(cudaMemset(h->y32, 0, M * d * 4));
   CK(cudaMemset(h->logits, 0, M * kLogitLd * 4));
   h->cap = n_layouts;
+  h->ws_generation++;
   int rc;
   if ((rc = make_map(&h->m_x16, h->x16, M, d, kBM, h->bf16))) return rc;
   if ((rc = make_map(&h->m_att16, h->att16, M, kAttN, kBM, h->bf16))) return rc;   // attention's TMA store target and the out-projection's A operand
@@ -418,7 +428,7 @@ int validate_common(LdmHandle* h, int B, const LdmSampling* s) {
 
 int step_impl(LdmHandle* h, int B, const long long* ids_in, int t_model, int t_post, const LdmCond* cond, const LdmSampling* samp,
               uint64_t seed, uint32_t step_ctr, int64_t b_global0, long long* ids_out, float* logits_out, float* logprob_out,
-              const float* logits_in, const float* logprob_in, cudaStream_t st) {
+              const float* logits_in, const float* logprob_in, cudaStream_t st, const unsigned long long* call = nullptr) {
   if (t_model < 0 || t_model >= h->T || t_post < 0 || t_post >= h->T)
     return fail(LDM_ERR_INVALID, "timestep out of range: t_model=%d t_post=%d T=%d (constrained.py:139)", t_model, t_post, h->T);
   int rc = ensure_workspace(h, B);
@@ -453,7 +463,7 @@ int step_impl(LdmHandle* h, int B, const long long* ids_in, int t_model, int t_p
                    ((cond->seq_orig && cond->refine_table) ? COND_REFINE : 0);
   }
   p.mode = samp->mode; p.temperature = samp->temperature; p.top_p = samp->top_p; p.top_k = samp->top_k;
-  p.seed = seed; p.step_ctr = step_ctr; p.b_global0 = b_global0;
+  p.seed = seed; p.step_ctr = step_ctr; p.b_global0 = b_global0; p.call = call;
   p.ids_out = ids_out; p.logprob_out = logprob_out;
   const int warps = B * h->S, blocks = (warps * 32 + 255) / 256;
   {
@@ -501,6 +511,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   if (const char* e = getenv("LDM_GEMM_DEBUG")) h->gemm_dbg = atoi(e);
   if (const char* e = getenv("LDM_GENERIC_POSTERIOR")) h->debug_generic_posterior = atoi(e);
   if (const char* e = getenv("LDM_PDL")) h->pdl = atoi(e);
+  if (const char* e = getenv("LDM_GRAPH")) h->use_graph = atoi(e);
 #define TRY(x) do { rc = (x); if (rc) { ldm_destroy(h); return rc; } } while (0)
 
   TRY(dev_upload(h, &h->cat_emb, w->cat_emb, static_cast<size_t>(C) * d));
@@ -576,6 +587,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
     }
     TRY(dev_upload(h, &h->sched, sch.data(), sch.size()));
     TRY(dev_alloc(h, &h->lae, static_cast<size_t>(h->G) * (T + 1) * 4));
+    TRY(dev_alloc(h, &h->call_block, static_cast<size_t>(2)));
     lae_table_kernel<<<(h->G * (T + 1) + 127) / 128, 128>>>(h->sched, h->lae, h->G, T + 1);
     if (cudaGetLastError() != cudaSuccess) { ldm_destroy(h); return fail(LDM_ERR_CUDA, "lae_table_kernel launch failed"); }
   }
@@ -619,6 +631,8 @@ int ldm_destroy(LdmHandle* h) {
   if (!h) return LDM_OK;
   cudaSetDevice(h->desc.device);
   cudaDeviceSynchronize();
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (void* p : h->owned) cudaFree(p);
   free_staging(h);
   free_workspace(h);
@@ -638,22 +652,15 @@ int ldm_step(LdmHandle* h, int32_t B, const int64_t* ids_in, int32_t t_model, in
                    reinterpret_cast<long long*>(ids_out), logits_out, logprob_out, logits_in, logprob_in, static_cast<cudaStream_t>(stream));
 }
 
-int ldm_sample_loop(LdmHandle* h, int32_t B, int32_t n_steps, const int32_t* t_model, const int32_t* t_post, const LdmCond* cond,
-                    const LdmSampling* sampling, uint64_t seed, int64_t b_global0, const int64_t* ids_init, int64_t* ids_out,
-                    int64_t* ids_trace, void* stream) {
-  int rc = validate_common(h, B, sampling);
-  if (rc) return rc;
-  if (n_steps < 1 || !t_model || !t_post || !ids_out) return fail(LDM_ERR_INVALID, "bad loop arguments");
-  for (int i = 0; i < n_steps; ++i) {
-    if (i > 0 && t_model[i] >= t_model[i - 1]) return fail(LDM_ERR_INVALID, "timesteps must be strictly decreasing (base.py:361-362 raises NotImplementedError)");
-  }
-  CK(cudaSetDevice(h->desc.device));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = ensure_workspace(h, B);
-  if (rc) return rc;
+namespace {
+
+// the plain loop: fill / pick the start state, then n_steps x step_impl on stream st
+int run_loop(LdmHandle* h, int B, int n_steps, const int32_t* t_model, const int32_t* t_post, const LdmCond* cond, const LdmSampling* sampling,
+             uint64_t seed, int64_t b_global0, const long long* ids_init, long long* ids_out, long long* ids_trace, cudaStream_t st,
+             const unsigned long long* call) {
   const size_t nid = static_cast<size_t>(B) * h->S;
   const long long* cur = nullptr;
-  if (ids_init) cur = reinterpret_cast<const long long*>(ids_init);
+  if (ids_init) cur = ids_init;
   else if (cond && cond->seq) cur = reinterpret_cast<const long long*>(cond->seq);
   else {
     ProfScope ps(h, CAT_MISC, st);
@@ -662,14 +669,97 @@ int ldm_sample_loop(LdmHandle* h, int32_t B, int32_t n_steps, const int32_t* t_m
   }
   for (int i = 0; i < n_steps; ++i) {
     long long* dst;
-    if (ids_trace) dst = reinterpret_cast<long long*>(ids_trace) + static_cast<size_t>(i) * nid;
-    else if (i == n_steps - 1) dst = reinterpret_cast<long long*>(ids_out);
+    if (ids_trace) dst = ids_trace + static_cast<size_t>(i) * nid;
+    else if (i == n_steps - 1) dst = ids_out;
     else dst = (cur == h->ids[0]) ? h->ids[1] : h->ids[0];
-    rc = step_impl(h, B, cur, t_model[i], t_post[i], cond, sampling, seed, static_cast<uint32_t>(i), b_global0, dst, nullptr, nullptr, nullptr, nullptr, st);
+    int rc = step_impl(h, B, cur, t_model[i], t_post[i], cond, sampling, seed, static_cast<uint32_t>(i), b_global0, dst, nullptr, nullptr, nullptr, nullptr, st, call);
     if (rc) return rc;
     cur = dst;
   }
   if (ids_trace) CK(cudaMemcpyAsync(ids_out, cur, nid * 8, cudaMemcpyDeviceToDevice, st));
+  return LDM_OK;
+}
+
+uint64_t fnv1a(uint64_t hsh, const void* data, size_t n) {
+  const unsigned char* b = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < n; ++i) { hsh ^= b[i]; hsh *= 1099511628211ull; }
+  return hsh;
+}
+
+}  // namespace
+
+int ldm_sample_loop(LdmHandle* h, int32_t B, int32_t n_steps, const int32_t* t_model, const int32_t* t_post, const LdmCond* cond,
+                    const LdmSampling* sampling, uint64_t seed, int64_t b_global0, const int64_t* ids_init, int64_t* ids_out,
+                    int64_t* ids_trace, void* stream) {
+  int rc = validate_common(h, B, sampling);
+  if (rc) return rc;
+  if (n_steps < 1 || !t_model || !t_post || !ids_out) return fail(LDM_ERR_INVALID, "bad loop arguments");
+  for (int i = 0; i < n_steps; ++i) {
+    if (t_model[i] < 0 || t_model[i] >= h->T || t_post[i] < 0 || t_post[i] >= h->T)
+      return fail(LDM_ERR_INVALID, "timestep out of range: t_model=%d t_post=%d T=%d (constrained.py:139)", t_model[i], t_post[i], h->T);
+    if (i > 0 && t_model[i] >= t_model[i - 1]) return fail(LDM_ERR_INVALID, "timesteps must be strictly decreasing (base.py:361-362 raises NotImplementedError)");
+  }
+  CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = ensure_workspace(h, B);
+  if (rc) return rc;
+  const size_t nid = static_cast<size_t>(B) * h->S;
+  const bool has_cond = cond && cond->seq;
+  if (!h->use_graph || h->prof || ids_trace || h->debug_stop_after)
+    return run_loop(h, B, n_steps, t_model, t_post, has_cond ? cond : nullptr, sampling, seed, b_global0, reinterpret_cast<const long long*>(ids_init),
+                    reinterpret_cast<long long*>(ids_out), reinterpret_cast<long long*>(ids_trace), st, nullptr);
+
+  // ---- CUDA-graph replay: the static T-step plan (n_steps x 23 launches with programmatic edges) is captured once; what changes
+  // from call to call is staged into handle-owned device buffers the captured kernels read ----
+  LdmCond gc{};
+  if (has_cond) {
+    if (reinterpret_cast<const long long*>(cond->seq) != h->c_seq) CK(cudaMemcpyAsync(h->c_seq, cond->seq, nid * 8, cudaMemcpyDeviceToDevice, st));
+    gc.seq = reinterpret_cast<const int64_t*>(h->c_seq);
+    if (cond->mask) {
+      if (cond->mask != h->c_mask) CK(cudaMemcpyAsync(h->c_mask, cond->mask, nid, cudaMemcpyDeviceToDevice, st));
+      gc.mask = h->c_mask;
+    }
+    if (cond->seq_orig && cond->refine_table) {
+      if (reinterpret_cast<const long long*>(cond->seq_orig) != h->c_seq_orig) CK(cudaMemcpyAsync(h->c_seq_orig, cond->seq_orig, nid * 8, cudaMemcpyDeviceToDevice, st));
+      const size_t tb = static_cast<size_t>(h->C) * h->C * 4;
+      if (!h->c_tbl) CK(cudaMalloc(reinterpret_cast<void**>(&h->c_tbl), tb));
+      if (cond->refine_table != h->c_tbl) CK(cudaMemcpyAsync(h->c_tbl, cond->refine_table, tb, cudaMemcpyDeviceToDevice, st));
+      gc.seq_orig = reinterpret_cast<const int64_t*>(h->c_seq_orig); gc.refine_table = h->c_tbl;
+    }
+    gc.pad_disable = cond->pad_disable;
+  }
+  if (ids_init && reinterpret_cast<const long long*>(ids_init) != h->ids[1]) CK(cudaMemcpyAsync(h->ids[1], ids_init, nid * 8, cudaMemcpyDeviceToDevice, st));
+  const unsigned long long blk[2] = {seed, static_cast<unsigned long long>(b_global0)};
+  CK(cudaMemcpyAsync(h->call_block, blk, sizeof(blk), cudaMemcpyHostToDevice, st));   // pageable source: staged by the driver before the call returns
+
+  uint64_t key = 1469598103934665603ull;
+  const int32_t head[6] = {B, n_steps, has_cond ? 1 + (gc.mask ? 2 : 0) + (gc.seq_orig ? 4 : 0) + (gc.pad_disable ? 8 : 0) : 0, ids_init ? 1 : 0, h->pdl, 0};
+  key = fnv1a(key, head, sizeof(head));
+  key = fnv1a(key, t_model, sizeof(int32_t) * n_steps);
+  key = fnv1a(key, t_post, sizeof(int32_t) * n_steps);
+  key = fnv1a(key, sampling, sizeof(LdmSampling));
+  key = fnv1a(key, &h->ws_generation, sizeof(h->ws_generation));
+  if (!h->graph_exec || key != h->graph_key) {
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    const int64_t l0 = h->launches;
+    CK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    rc = run_loop(h, B, n_steps, t_model, t_post, has_cond ? &gc : nullptr, sampling, 0, 0, ids_init ? h->ids[1] : nullptr, h->ids_final, nullptr,
+                  h->cap_stream, h->call_block);
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &g);
+    h->graph_launches = h->launches - l0;
+    h->launches = l0;                                  // counted per replay below
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (ce != cudaSuccess || !g) return fail(LDM_ERR_CUDA, "graph capture of the sampling loop failed: %s", cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(&h->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) { h->graph_exec = nullptr; return fail(LDM_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+    h->graph_key = key;
+  }
+  CK(cudaGraphLaunch(h->graph_exec, st));
+  h->launches += h->graph_launches;
+  if (reinterpret_cast<long long*>(ids_out) != h->ids_final) CK(cudaMemcpyAsync(ids_out, h->ids_final, nid * 8, cudaMemcpyDeviceToDevice, st));
   return LDM_OK;
 }
 

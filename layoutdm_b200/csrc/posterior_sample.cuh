@@ -30,6 +30,8 @@ struct StepParams {
   int cond_flags;
   int mode; float temperature; float top_p; int top_k;
   unsigned long long seed; unsigned int step_ctr; long long b_global0;
+  const unsigned long long* call;        // nullptr, or device words {seed, b_global0} that override the two fields above: a captured
+                                         // CUDA graph of the loop stays valid while the noise key changes from call to call
   long long* ids_out;                    // [n_layouts][S]
   float* logprob_out;                    // [n_layouts][S][C] or nullptr
 };
@@ -177,8 +179,9 @@ LDM_DEVINL void posterior_token_generic(const StepParams& p, const int token, co
 #pragma unroll
     for (int j = 0; j < 5; ++j) lg[j] = valid[j] ? lp[j] / p.temperature : -INFINITY;
 
-    const unsigned long long tok = (static_cast<unsigned long long>(p.b_global0) + b) * static_cast<unsigned long long>(p.S) + s;
-    const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
+    const unsigned long long seed = p.call ? __ldg(p.call) : p.seed, bg0 = p.call ? __ldg(p.call + 1) : static_cast<unsigned long long>(p.b_global0);
+    const unsigned long long tok = (bg0 + b) * static_cast<unsigned long long>(p.S) + s;
+    const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
     const uint32_t tok_lo = static_cast<uint32_t>(tok), tok_hi = static_cast<uint32_t>(tok >> 32);
     const uint32_t w1 = p.step_ctr & 0xFFFFFFu;
 
@@ -430,8 +433,9 @@ __global__ void __launch_bounds__(256) posterior_sample_group_kernel(const StepP
 #pragma unroll
       for (int j = 0; j < 2; ++j) if (on[j] && n_before[j] > 0 && static_cast<float>(cum[j]) > p.top_p) lg[j] = -INFINITY;
     }
-    const unsigned long long tok = (static_cast<unsigned long long>(p.b_global0) + b) * static_cast<unsigned long long>(p.S) + s;
-    const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
+    const unsigned long long seed = p.call ? __ldg(p.call) : p.seed, bg0 = p.call ? __ldg(p.call + 1) : static_cast<unsigned long long>(p.b_global0);
+    const unsigned long long tok = (bg0 + b) * static_cast<unsigned long long>(p.S) + s;
+    const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
     const uint32_t tok_lo = static_cast<uint32_t>(tok), tok_hi = static_cast<uint32_t>(tok >> 32);
     const uint32_t w1 = p.step_ctr & 0xFFFFFFu;
     // class c draws word c % 4 of Philox block c / 4.  One evaluation per noise stream serves the whole token: lanes 0..8
