@@ -81,6 +81,14 @@ typedef struct {
   const int64_t* seq_orig;     /* cond["seq_orig"] (refinement) or NULL */
   const float* refine_table;   /* [C][C], already multiplied by +-refine_lambda (task.py:154-224) or NULL */
   int32_t pad_disable;         /* 1 for cond types c / cwh / refinement / relation (base.py:272-284) */
+  /* cond = "relation" (base.py:261-269): gradient-based logit adjustment between the posterior and the draw, replacing
+   * `update` (logit_adjustment.py:88-126; relation_mode "average").  rel_adj == NULL: off. */
+  const int32_t* rel_adj;      /* [B][1+n_elem][1+n_elem] edge_attr bit masks (data/util.py:14-27) of the edge i -> j of
+                                  cond["batch_w_canvas"], node 0 = canvas (AddCanvasElement), 0 = no edge */
+  const float* rel_centers;    /* [4][n_bins] bbox bin centres (x, y, w, h) or NULL = linear quantisation */
+  float rel_lambda;            /* sampling_cfg.relation_lambda: SGD learning rate (logit_adjustment.py:101-103) */
+  int32_t rel_num_update;      /* sampling_cfg.relation_num_update (applied for t_model >= 10 only, :105) */
+  int32_t rel_batch_total;     /* batch size the reference's loss.mean() runs over (the GLOBAL batch when sharded); <= 0: B */
 } LdmCond;
 
 /* helpers/sampling.py:13-59 */
@@ -109,7 +117,8 @@ int ldm_destroy(LdmHandle* h);
  *   logits_out_dev  [B][S][C] fp32  denoiser logits                 (CategoricalTransformer.forward, nn_lib.py:191-237)
  *   logprob_out_dev [B][S][C] fp32  log p(x_{t-1}|x_t) after the cond adjustments (input of sample(), base.py:287)
  *   logits_in_dev   [B][S][C] fp32  skip the denoiser and use these logits
- *   logprob_in_dev  [B][S][C] fp32  skip everything but the draw (hook for cond=relation, logit_adjustment.py:88-126) */
+ *   logprob_in_dev  [B][S][C] fp32  skip everything but [PAD-disable when cond->pad_disable, base.py:271-284, and] the draw
+ *                                   (hook for an external logit adjustment such as the reference's own `update`) */
 int ldm_step(LdmHandle* h, int32_t B, const int64_t* ids_in_dev, int32_t t_model, int32_t t_post,
              const LdmCond* cond, const LdmSampling* sampling, uint64_t seed, uint32_t step_ctr, int64_t b_global0,
              int64_t* ids_out_dev, float* logits_out_dev, float* logprob_out_dev,

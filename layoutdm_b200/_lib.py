@@ -29,7 +29,9 @@ class LdmWeights(C.Structure):
 
 class LdmCond(C.Structure):
     _fields_ = [("seq", C.c_void_p), ("mask", C.c_void_p), ("seq_orig", C.c_void_p), ("refine_table", C.c_void_p),
-                ("pad_disable", C.c_int32)]
+                ("pad_disable", C.c_int32),
+                ("rel_adj", C.c_void_p), ("rel_centers", C.c_void_p), ("rel_lambda", C.c_float), ("rel_num_update", C.c_int32),
+                ("rel_batch_total", C.c_int32)]
 
 
 class LdmSampling(C.Structure):

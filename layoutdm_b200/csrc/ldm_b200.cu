@@ -18,6 +18,7 @@
 #include "embed.cuh"
 #include "gemm_tc.cuh"
 #include "posterior_sample.cuh"
+#include "relation.cuh"
 
 using namespace ldm;
 
@@ -145,6 +146,7 @@ struct LdmHandle {
   int cap = 0;
   void *x16 = nullptr, *qkv16 = nullptr, *att16 = nullptr, *z16 = nullptr, *hid16 = nullptr;
   float *x32 = nullptr, *y32 = nullptr, *logits = nullptr;
+  float* rel_lp = nullptr;      // [cap][S][C] log-probabilities between the posterior and the draw (cond = relation)
   unsigned long long* ln_stats = nullptr; unsigned ln_epoch = 0;   // LN statistics exchange between CTA pairs (gemm_tc.cuh)
   long long* ids[2] = {nullptr, nullptr};
   long long* ids_final = nullptr;
@@ -279,7 +281,7 @@ void free_workspace(LdmHandle* h) {
   void** ws[] = {&h->x16, &h->qkv16, &h->att16, &h->z16, &h->hid16, reinterpret_cast<void**>(&h->x32), reinterpret_cast<void**>(&h->y32),
                  reinterpret_cast<void**>(&h->logits), reinterpret_cast<void**>(&h->ids[0]), reinterpret_cast<void**>(&h->ids[1]),
                  reinterpret_cast<void**>(&h->ids_final), reinterpret_cast<void**>(&h->c_seq), reinterpret_cast<void**>(&h->c_seq_orig),
-                 reinterpret_cast<void**>(&h->c_mask), reinterpret_cast<void**>(&h->ln_stats)};
+                 reinterpret_cast<void**>(&h->c_mask), reinterpret_cast<void**>(&h->ln_stats), reinterpret_cast<void**>(&h->rel_lp)};
   for (void** p : ws) { if (*p) cudaFree(*p); *p = nullptr; }
   h->cap = 0;
 }
@@ -466,6 +468,40 @@ int step_impl(LdmHandle* h, int B, const long long* ids_in, int t_model, int t_p
   p.seed = seed; p.step_ctr = step_ctr; p.b_global0 = b_global0; p.call = call;
   p.ids_out = ids_out; p.logprob_out = logprob_out;
   const int warps = B * h->S, blocks = (warps * 32 + 255) / 256;
+  // cond = relation on the device (base.py:243-284 order: strong mask [+ refinement prior] -> update() -> PAD-disable -> draw):
+  //   1. posterior kernel -> log-probs with PAD-disable OFF into rel_lp   2. relation_update_kernel in place
+  //   3. draw kernel from rel_lp with PAD-disable.  `update` does nothing for t < 10 (logit_adjustment.py:105): plain path then.
+  const bool relation = cond && cond->seq && cond->rel_adj && logprob_in == nullptr && cond->rel_num_update > 0 && t_model >= 10;
+  if (relation) {
+    if (h->desc.n_attr != 5 || h->desc.n_elem + 1 > kRelMaxNodes || h->desc.n_bins > 32)
+      return fail(LDM_ERR_UNSUPPORTED, "relation update needs the c-x-y-w-h layout with <= 31 elements and <= 32 bins");
+    if (!h->rel_lp) CK(cudaMalloc(reinterpret_cast<void**>(&h->rel_lp), static_cast<size_t>(h->cap) * h->S * h->C * sizeof(float)));
+    StepParams p1 = p;
+    p1.cond_flags &= ~COND_PAD_DISABLE; p1.logprob_out = h->rel_lp;
+    {
+      ProfScope ps(h, CAT_EPILOGUE, st);
+      CK(launch_step(h, posterior_sample_kernel, blocks, 256, 0, st, false, p1));
+    }
+    RelationParams r{};
+    r.n_layouts = B; r.S = h->S; r.C = h->C; r.n_attr = h->desc.n_attr; r.n_elem = h->desc.n_elem; r.n_cat = h->desc.n_cat;
+    r.n_bins = h->desc.n_bins; r.pad_id = h->C - 2; r.lp = h->rel_lp; r.cond_seq = p.cond_seq; r.adj = cond->rel_adj; r.centers = cond->rel_centers;
+    const int btot = cond->rel_batch_total > 0 ? cond->rel_batch_total : B;
+    r.step = cond->rel_lambda / static_cast<float>(btot * 14);            // len(const.relation) = 14 cost functions (const.py:226-241)
+    r.n_update = cond->rel_num_update;
+    {
+      ProfScope ps(h, CAT_EPILOGUE, st);
+      CK(launch_step(h, relation_update_kernel, B, kRelThreads, 0, st, false, r));
+    }
+    StepParams p2 = p;
+    p2.logprob_in = h->rel_lp;
+    p2.logprob_out = logprob_out;            // tap: the adjusted log-probs after PAD-disable (what sample() sees, base.py:287)
+    {
+      ProfScope ps(h, CAT_EPILOGUE, st);
+      CK(launch_step(h, posterior_sample_kernel, blocks, 256, 0, st, false, p2));
+    }
+    CK(cudaGetLastError());
+    return LDM_OK;
+  }
   {
     ProfScope ps(h, CAT_EPILOGUE, st);
     bool group_path = p.constrained && p.logprob_in == nullptr && p.logprob_out == nullptr &&
@@ -705,7 +741,7 @@ int ldm_sample_loop(LdmHandle* h, int32_t B, int32_t n_steps, const int32_t* t_m
   if (rc) return rc;
   const size_t nid = static_cast<size_t>(B) * h->S;
   const bool has_cond = cond && cond->seq;
-  if (!h->use_graph || h->prof || ids_trace || h->debug_stop_after)
+  if (!h->use_graph || h->prof || ids_trace || h->debug_stop_after || (has_cond && cond->rel_adj))
     return run_loop(h, B, n_steps, t_model, t_post, has_cond ? cond : nullptr, sampling, seed, b_global0, reinterpret_cast<const long long*>(ids_init),
                     reinterpret_cast<long long*>(ids_out), reinterpret_cast<long long*>(ids_trace), st, nullptr);
 

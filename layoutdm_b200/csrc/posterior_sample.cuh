@@ -72,6 +72,12 @@ LDM_DEVINL void posterior_token_generic(const StepParams& p, const int token, co
   if (p.logprob_in != nullptr) {
 #pragma unroll
     for (int j = 0; j < 5; ++j) lp[j] = valid[j] ? p.logprob_in[static_cast<size_t>(token) * C + cls[j]] : -INFINITY;
+    // the log-probs were adjusted outside (cond = relation: base.py:261-269); what is left of the reference's order is disabling
+    // PAD where the number of elements is known (base.py:271-284)
+    if ((p.cond_flags & COND_PAD_DISABLE) && (s % p.n_attr != 0) && p.cond_seq[token] != p.pad_id) {
+#pragma unroll
+      for (int j = 0; j < 5; ++j) if (valid[j] && cls[j] == p.pad_id) lp[j] = kLogEps;
+    }
   } else {
     // ---- predict_start: float64 log-softmax over the C-1 non-MASK classes, clamp [-70, 0] ----
     const float* lrow = p.logits + (static_cast<size_t>(b) * 128 + s) * p.ld_logits;

@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from .engine import Engine, sampling_struct
-from .vocab import Vocab, decode_ids, linear_centers, refinement_table, timestep_plan
+from .vocab import Vocab, decode_ids, linear_centers, refinement_table, relation_edge_table, timestep_plan
 
 
 def _cfg_get(cfg, key, default=None):
@@ -42,7 +42,7 @@ def duplicate_cond(cond: Dict, batch_size: int) -> Dict:
     refinement band table is shared by all layouts and stays as it is."""
     if cond["seq"].size(0) == 1 and batch_size > 1:
         for k in cond:
-            if isinstance(cond[k], torch.Tensor) and k != "refine_table":
+            if isinstance(cond[k], torch.Tensor) and k not in ("refine_table", "rel_centers"):
                 cond[k] = cond[k].repeat([batch_size] + [1] * (cond[k].dim() - 1))
     return cond
 
@@ -63,6 +63,7 @@ class FusedMaskAndReplaceDiffusion:
         self._step_ctr = 0
         self._seed: Optional[int] = None     # noise key of `_sample_single_step` trajectories (None: drawn from torch's generator)
         self._last_t: Optional[int] = None
+        self.relation_on_device = True   # cond=relation, relation_mode "average": hand-derived update kernel; False: logit_adjust_fn hook
         self.logit_adjust_fn = None      # optional hook f(t: int, cond, model_log_prob (B,C,S), sampling_cfg) for cond=relation
 
     @property
@@ -79,6 +80,15 @@ class FusedMaskAndReplaceDiffusion:
             cond["refine_table"] = refinement_table(self.vocab, self.bbox_centers, _cfg_get(sampling_cfg, "refine_mode", "uniform"),
                                                     _cfg_get(sampling_cfg, "refine_offset_ratio", 0.1),
                                                     _cfg_get(sampling_cfg, "refine_lambda", 3.0))
+        if self.relation_on_device and cond.get("type") == "relation" and "batch_w_canvas" in cond and "rel_adj" not in cond \
+                and _cfg_get(sampling_cfg, "relation_mode", "average") == "average" and float(_cfg_get(sampling_cfg, "relation_lambda", 0.0)) > 0.0:
+            # logit_adjustment.update (:88-126) on the device: dense edge table + bin centres + SGD hyper-parameters.
+            # relation_mode "gumbel" draws torch noise inside the update and stays on the reference's autograd path (logit_adjust_fn).
+            cond["rel_adj"] = relation_edge_table(cond["batch_w_canvas"], cond["seq"].size(0), self.vocab.n_elem + 1)
+            cond["rel_centers"] = torch.stack([torch.as_tensor(c, dtype=torch.float32).view(-1) for c in self.bbox_centers])
+            cond["rel_lambda"] = float(_cfg_get(sampling_cfg, "relation_lambda", 3e6))
+            cond["rel_num_update"] = int(_cfg_get(sampling_cfg, "relation_num_update", 3))
+            cond.setdefault("rel_batch_total", batch_size)
         cond = duplicate_cond(cond, batch_size)
         for k in list(cond):
             if isinstance(cond[k], torch.Tensor):
@@ -103,7 +113,8 @@ class FusedMaskAndReplaceDiffusion:
             assert cond_d["seq"].shape[0] == batch_size
             assert cond_d["seq"].max().item() < self.num_classes
         seed = self._new_seed() if seed is None else seed
-        if cond_d is not None and cond_d.get("type") == "relation":
+        if cond_d is not None and cond_d.get("type") == "relation" and "rel_adj" not in cond_d and self.logit_adjust_fn is not None:
+            # an external (Python) logit adjustment between posterior and draw: per-step host loop through the log-prob taps
             return self._sample_stepwise(batch_size, plan, cond_d, sampling_cfg, seed, b_global0, get_intermediate_results)
         res = self.engine.sample_loop(batch_size, plan, sampling_cfg, cond_d, seed=seed, b_global0=b_global0, trace=get_intermediate_results)
         if get_intermediate_results:
@@ -121,7 +132,7 @@ class FusedMaskAndReplaceDiffusion:
         return results if trace else ids.cpu()
 
     def _step_ids(self, ids, t_model, t_post, sampling_cfg, cond, seed, step_ctr, b_global0=0):
-        if cond is not None and cond.get("type") == "relation" and self.logit_adjust_fn is not None:
+        if cond is not None and cond.get("type") == "relation" and "rel_adj" not in cond and self.logit_adjust_fn is not None:
             # base.py:243-284 order: strong mask -> update() -> PAD-disable -> draw.  The first call returns the log-probs with the
             # strong mask only (PAD-disable off: `update` must see what the reference's sees), the hook edits them, PAD-disable
             # is applied here, the second call draws from the result.  `t` is an int like in the reference (base.py:262).

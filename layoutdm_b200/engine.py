@@ -153,6 +153,19 @@ class Engine:
             assert tb.shape == (self.vocab.C, self.vocab.C), f"refine_table must be (C, C) = ({self.vocab.C}, {self.vocab.C}), got {tuple(tb.shape)}"
             c.seq_orig, c.refine_table = so.data_ptr(), tb.data_ptr()
         c.pad_disable = 1 if cond.get("type") in ("c", "cwh", "refinement", "relation") else 0   # base.py:272
+        if cond.get("rel_adj") is not None and int(cond.get("rel_num_update", 0)) > 0:
+            # cond = relation on the device (logit_adjustment.py:88-126): dense edge table, bin centres, SGD hyper-parameters
+            E1 = self.vocab.n_elem + 1
+            adj = cond["rel_adj"].to(self.device, torch.int32).contiguous(); keep.append(adj)
+            assert adj.shape == (seq.shape[0], E1, E1), f"rel_adj must be (B, {E1}, {E1}), got {tuple(adj.shape)}"
+            c.rel_adj = adj.data_ptr()
+            if cond.get("rel_centers") is not None:
+                cen = cond["rel_centers"].to(self.device, torch.float32).contiguous(); keep.append(cen)
+                assert cen.shape == (4, self.vocab.n_bins)
+                c.rel_centers = cen.data_ptr()
+            c.rel_lambda = float(cond["rel_lambda"])
+            c.rel_num_update = int(cond["rel_num_update"])
+            c.rel_batch_total = int(cond.get("rel_batch_total", 0) or 0)
         if cond.get("_pad_disable") is not None:                     # relation hook: PAD-disable comes after update() (base.py:261-284)
             c.pad_disable = 1 if cond["_pad_disable"] else 0
         return c, keep

@@ -22,7 +22,7 @@ def shard_cond(cond: Optional[Dict], lo: int, hi: int) -> Optional[Dict]:
         return None
     out = {}
     for k, v in cond.items():
-        if isinstance(v, torch.Tensor) and v.dim() >= 1 and k != "refine_table":
+        if isinstance(v, torch.Tensor) and v.dim() >= 1 and k not in ("refine_table", "rel_centers"):
             out[k] = v[lo:hi] if v.shape[0] > 1 else v          # a single condition broadcasts (task.py:235-248)
         else:
             out[k] = v

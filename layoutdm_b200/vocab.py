@@ -115,3 +115,19 @@ def decode_ids(ids: torch.Tensor, vocab: Vocab, centers: Optional[Sequence[np.nd
     label[invalid] = 0
     out[invalid] = 0.0
     return {"bbox": out, "label": label, "mask": ~invalid}
+
+
+def relation_edge_table(batch, n_layouts: int, n_slots: int) -> torch.Tensor:
+    """cond["batch_w_canvas"] (the PyG batch `get_cond(..., "relation")` attaches, helpers/task.py:112-114; node 0 of every
+    layout is the canvas, data/util.py:106-120) -> dense (B, n_slots, n_slots) int32 table of its edge_attr bit masks
+    (RelSize / RelLoc, data/util.py:14-27): table[b, i, j] = attr of the edge i -> j, 0 = no edge.  This is what LdmCond.rel_adj takes."""
+    tab = torch.zeros(n_layouts, n_slots, n_slots, dtype=torch.int32)
+    ei = getattr(batch, "edge_index", None)
+    if ei is None or ei.numel() == 0:
+        return tab
+    ei, ea, bv = ei.cpu().long(), batch.edge_attr.cpu(), batch.batch.cpu().long()
+    num = torch.zeros(n_layouts, dtype=torch.long).scatter_add_(0, bv, torch.ones_like(bv))
+    first = torch.cat([num.new_zeros(1), num.cumsum(0)])
+    b = bv[ei[0]]
+    tab[b, ei[0] - first[b], ei[1] - first[b]] = ea.to(torch.int32)
+    return tab

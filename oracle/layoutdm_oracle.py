@@ -367,9 +367,10 @@ def linear_centers(n_bins: int = 32) -> List[np.ndarray]:
     return [xy, xy, wh, wh]
 
 
-def cond_adjust(logp: torch.Tensor, vocab: VocabSpec, cond: Optional[dict]) -> torch.Tensor:
-    """base.py:243-284 without the `relation` branch.  cond: seq (B,S), mask (B,S) bool, type,
-    optional seq_orig + refine_table (C,C) already multiplied by refine_lambda."""
+def cond_adjust(logp: torch.Tensor, vocab: VocabSpec, cond: Optional[dict], t_model: Optional[int] = None) -> torch.Tensor:
+    """base.py:243-284.  cond: seq (B,S), mask (B,S) bool, type, optional seq_orig + refine_table (C,C) already multiplied by
+    refine_lambda; for type "relation" (:261-269) optional rel_adj (B,1+E,1+E) int edge table, rel_lambda, rel_num_update,
+    rel_centers (4, n_bins) [default linear], rel_batch_total -- applied with relation_update when t_model is given."""
     if not cond:
         return logp
     logp = logp.clone()
@@ -380,6 +381,12 @@ def cond_adjust(logp: torch.Tensor, vocab: VocabSpec, cond: Optional[dict]) -> t
     if cond.get("type") == "refinement":                                  # :254-258
         weak = cond["refine_table"][cond["seq_orig"]]                     # (B,S,C)  F.embedding, task.py:200
         logp = torch.where(cond["mask"][..., None], logp, logp + weak)
+    if cond.get("type") == "relation" and cond.get("rel_adj") is not None and t_model is not None:   # :261-269
+        cen = cond.get("rel_centers")
+        if cen is None:
+            cen = torch.stack([torch.as_tensor(c, dtype=torch.float32) for c in linear_centers(vocab.n_bins)])
+        logp = relation_update(logp, cond["seq"], cond["rel_adj"], cen, vocab, t_model, cond["rel_lambda"], cond["rel_num_update"],
+                               batch_total=cond.get("rel_batch_total"))
     if cond["type"] in ("c", "cwh", "refinement", "relation"):            # :272-284
         S = cond["seq"].shape[1]
         pad_mask = (torch.arange(S)[None] % vocab.n_attr != 0) & (cond["seq"] != vocab.pad_id)
@@ -509,12 +516,12 @@ class Oracle:
 
     def step_logprob(self, x_t: torch.Tensor, t_model: int, t_post: int, cond: Optional[dict] = None):
         logits = denoiser_forward(self.sd, x_t, t_model, self.vocab, self.spec, self.operand_dtype)
-        return self.logprob_from_logits(logits, x_t, t_post, cond), logits
+        return self.logprob_from_logits(logits, x_t, t_post, cond, t_model), logits
 
-    def logprob_from_logits(self, logits, x_t, t_post, cond=None):
+    def logprob_from_logits(self, logits, x_t, t_post, cond=None, t_model=None):
         lx0 = predict_start(logits)
         lp = q_posterior(lx0, x_t, t_post, self.spec.T, self.vocab, self.scheds, self.q_type)
-        return cond_adjust(lp, self.vocab, cond)
+        return cond_adjust(lp, self.vocab, cond, t_model)
 
     def sample(self, B: int, cfg: SamplingCfg, seed: int = 0, cond: Optional[dict] = None,
                b_global0: int = 0, trace: Optional[list] = None) -> torch.Tensor:
@@ -646,3 +653,143 @@ def q_sample_ids(x0: torch.Tensor, t: torch.Tensor, T: int, vocab: VocabSpec, sc
         k = (gumbel[:, sl][..., idx] + logits).argmax(dim=-1)
         out[:, sl] = idx[k]
     return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# cond=relation: gradient-based logit adjustment  (T/models/categorical_diffusion/logit_adjustment.py:16-126,
+# losses T/models/clg/const.py:53-243, relation codes T/data/util.py:14-30)
+# --------------------------------------------------------------------------------------------------------------
+REL_SIZE_SM, REL_SIZE_EQ, REL_SIZE_LG = 1, 2, 3                     # RelSize  (data/util.py:14-18)
+REL_LOC_L, REL_LOC_T, REL_LOC_R, REL_LOC_B, REL_LOC_C = 5, 6, 7, 8, 9   # RelLoc   (data/util.py:21-27)
+REL_SIZE_ALPHA = 0.1                                                # data/util.py:30
+N_REL_FUNCS = 14                                                    # len(const.relation), const.py:226-241
+
+
+def relation_adjacency(edge_index: torch.Tensor, edge_attr: torch.Tensor, batch: torch.Tensor, B: int, n_slots: int) -> torch.Tensor:
+    """PyG-style edges of a batch WITH canvas nodes (AddCanvasElement, data/util.py:106-120: node 0 of every layout is the
+    canvas) -> dense (B, n_slots, n_slots) int32 bit masks: adj[b, i, j] = edge_attr of the edge i -> j (slot 0 = canvas)."""
+    adj = torch.zeros(B, n_slots, n_slots, dtype=torch.int32)
+    if edge_index.numel() == 0:
+        return adj
+    num = torch.zeros(B, dtype=torch.long).scatter_add_(0, batch, torch.ones_like(batch))
+    cum = torch.cat([num.new_zeros(1), num.cumsum(0)])
+    b = batch[edge_index[0]]
+    adj[b, edge_index[0] - cum[b], edge_index[1] - cum[b]] = edge_attr.to(torch.int32)
+    return adj
+
+
+def relation_bbox(lp: torch.Tensor, cond_seq: torch.Tensor, centers: torch.Tensor, vocab: VocabSpec):
+    """_stochastic_convert, mode='average' (logit_adjustment.py:16-85): expected box of every node.
+    lp (B,S,C) log-probs, centers (4, n_bins) -> p (B, 1+E, 4, n_bins), bbox (B, 1+E, 4) xywh, valid (B, 1+E); node 0 = canvas,
+    whose logits are the log one-hot of encode([0.5, 0.5, 1, 1]) (:36-41)."""
+    B = lp.shape[0]
+    E, A, nb, nc = vocab.n_elem, vocab.n_attr, vocab.n_bins, vocab.n_cat
+    logits = torch.empty(B, 1 + E, 4, nb, dtype=lp.dtype)
+    d = 1.0 / nb
+    canvas = torch.tensor([0.5, 0.5, 1.0, 1.0])
+    q = torch.cat([canvas[:2].clamp(0.0, 1.0 - d), canvas[2:].clamp(d, 1.0) - d])          # bbox_tokenizer.py:88-93 (linear)
+    cb = (nb * q).round().long()
+    if centers is not None and not torch.allclose(centers, torch.stack([torch.as_tensor(c, dtype=torch.float32) for c in linear_centers(nb)])):
+        cb = (canvas[:, None] - centers).pow(2).argmin(dim=1)                               # KMeans.predict (:95-104)
+    for a in range(4):
+        lo = nc + a * nb
+        logits[:, 1:, a] = lp[:, (a + 1)::A, lo:lo + nb]
+        logits[:, 0, a] = torch.log(F.one_hot(cb[a], nb).float().clamp(min=1e-30))
+    valid = torch.cat([torch.ones(B, 1, dtype=torch.bool), cond_seq[:, ::A] != vocab.pad_id], dim=1)
+    p = torch.softmax(logits, dim=-1)
+    bbox = (p * centers[None, None]).sum(-1)
+    return p, bbox, valid
+
+
+def relation_cost_and_grad(bbox: torch.Tensor, valid: torch.Tensor, adj: torch.Tensor):
+    """The 14 relation costs of const.py:226-241 summed per layout, and d(sum)/d(bbox) by hand (ReLU subgradient 0 at 0, as
+    autograd's).  bbox (B,N,4) xywh, adj (B,N,N) edge bit masks -> cost (B,), grad (B,N,4).  Plain loops: test sizes only."""
+    B, N, _ = bbox.shape
+    cost = torch.zeros(B, dtype=torch.float32)
+    grad = torch.zeros_like(bbox)
+    eps = torch.tensor(1e-8, dtype=torch.float32)
+    al, ah = torch.tensor(1 - REL_SIZE_ALPHA, dtype=torch.float32), torch.tensor(1 + REL_SIZE_ALPHA, dtype=torch.float32)
+    third, two3 = torch.tensor(1.0 / 3, dtype=torch.float32), torch.tensor(2.0 / 3, dtype=torch.float32)
+    for b in range(B):
+        x, y, w, h = bbox[b].unbind(-1)
+        area = w * h
+        l, t, r, bt = x - w / 2, y - h / 2, x + w / 2, y + h / 2
+        g_area = torch.zeros(N); g_l = torch.zeros(N); g_t = torch.zeros(N); g_r = torch.zeros(N); g_b = torch.zeros(N); g_y = torch.zeros(N)
+
+        def relu_term(v, pos, neg):
+            """cost += relu(v); where v > 0 the listed (tensor, index, coefficient) gradient entries are applied"""
+            nonlocal cost
+            if v > 0:
+                cost[b] += v
+                for arr, idx, coef in pos + neg:
+                    arr[idx] += coef
+        for i in range(N):
+            for j in range(N):
+                m = int(adj[b, i, j])
+                if m == 0 or not (valid[b, i] and valid[b, j]):
+                    continue
+                ai, aj = area[i], area[j]
+                if m & (1 << REL_SIZE_SM):                                   # const.py:73-79: a_j <= (1 - alpha) a_i
+                    relu_term(aj - al * ai, [(g_area, j, 1.0)], [(g_area, i, -float(al))])
+                if m & (1 << REL_SIZE_EQ):                                   # :82-89
+                    relu_term(al * ai - aj + eps, [(g_area, i, float(al))], [(g_area, j, -1.0)])
+                    relu_term(aj - ah * ai + eps, [(g_area, j, 1.0)], [(g_area, i, -float(ah))])
+                if m & (1 << REL_SIZE_LG):                                   # :92-98
+                    relu_term(ah * ai - aj, [(g_area, i, float(ah))], [(g_area, j, -1.0)])
+                if i == 0:                                                   # source is the canvas (y == 0): :101-148
+                    yc = y[j]
+                    if m & (1 << REL_LOC_T):
+                        relu_term(yc - third, [(g_y, j, 1.0)], [])
+                    if m & (1 << REL_LOC_C):
+                        relu_term(third - yc + eps, [], [(g_y, j, -1.0)])
+                        relu_term(yc - two3 + eps, [(g_y, j, 1.0)], [])
+                    if m & (1 << REL_LOC_B):
+                        relu_term(two3 - yc, [], [(g_y, j, -1.0)])
+                else:                                                        # :150-223
+                    if m & (1 << REL_LOC_T):
+                        relu_term(bt[j] - t[i], [(g_b, j, 1.0)], [(g_t, i, -1.0)])
+                    if m & (1 << REL_LOC_B):
+                        relu_term(bt[i] - t[j], [(g_b, i, 1.0)], [(g_t, j, -1.0)])
+                    for code in (REL_LOC_L, REL_LOC_R, REL_LOC_C):
+                        if not m & (1 << code):
+                            continue
+                        if code == REL_LOC_L:
+                            relu_term(r[j] - l[i], [(g_r, j, 1.0)], [(g_l, i, -1.0)])
+                        elif code == REL_LOC_R:
+                            relu_term(r[i] - l[j], [(g_r, i, 1.0)], [(g_l, j, -1.0)])
+                        else:
+                            relu_term(l[i] - r[j] + eps, [(g_l, i, 1.0)], [(g_r, j, -1.0)])
+                            relu_term(l[j] - r[i] + eps, [(g_l, j, 1.0)], [(g_r, i, -1.0)])
+                        relu_term(t[i] - bt[j] + eps, [(g_t, i, 1.0)], [(g_b, j, -1.0)])     # :168-170: t1 < b2 and t2 < b1
+                        relu_term(t[j] - bt[i] + eps, [(g_t, j, 1.0)], [(g_b, i, -1.0)])
+        grad[b, :, 0] = g_l + g_r
+        grad[b, :, 1] = g_t + g_b + g_y
+        grad[b, :, 2] = g_area * h + (g_r - g_l) / 2
+        grad[b, :, 3] = g_area * w + (g_b - g_t) / 2
+    return cost, grad
+
+
+def relation_update(lp: torch.Tensor, cond_seq: torch.Tensor, adj: torch.Tensor, centers: torch.Tensor, vocab: VocabSpec, t: int,
+                    relation_lambda: float, relation_num_update: int, mode: str = "average", batch_total: Optional[int] = None) -> torch.Tensor:
+    """`update` (logit_adjustment.py:88-126) without autograd: `relation_num_update` SGD steps (lr = relation_lambda, :101-103) on
+    the (B,S,C) log-probs for the loss mean_{b, f}(cost_f,b) (:117-120); no update for t < 10 (:105).  Returns the new log-probs."""
+    if mode != "average":
+        raise NotImplementedError("relation_mode 'gumbel' draws torch noise inside the update (logit_adjustment.py:76-77)")
+    lp = lp.clone()
+    n_up = 0 if t < 10 else relation_num_update
+    B = lp.shape[0]
+    A, nb, nc = vocab.n_attr, vocab.n_bins, vocab.n_cat
+    has_edges = bool((adj != 0).any())
+    for _ in range(n_up):
+        if not has_edges:                                                    # :113-115
+            continue
+        p, bbox, valid = relation_bbox(lp, cond_seq, centers, vocab)
+        _, g = relation_cost_and_grad(bbox, valid, adj)
+        g = g / float((batch_total or B) * N_REL_FUNCS)                      # torch.stack(loss, -1).mean() over (layouts, costs)
+        # d bbox_a / d logit_c = p_c (center_c - bbox_a)   (softmax over the attribute's bins, :74-85)
+        dlog = g[..., None] * p * (centers[None, None] - bbox[..., None])    # (B, 1+E, 4, nb)
+        dlog = dlog * valid[..., None, None]
+        for a in range(4):
+            lo = nc + a * nb
+            lp[:, (a + 1)::A, lo:lo + nb] -= relation_lambda * dlog[:, 1:, a]
+    return lp

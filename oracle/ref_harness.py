@@ -93,7 +93,11 @@ class FakeBatch:
         self.attr = {"has_canvas_element": False}
 
     def to(self, device):
-        return self
+        """like torch_geometric's Batch.to: every tensor attribute moves"""
+        out = FakeBatch.__new__(FakeBatch)
+        for k, v in self.__dict__.items():
+            setattr(out, k, v.to(device) if isinstance(v, torch.Tensor) else v)
+        return out
 
 
 def synthetic_layouts(B: int, n_cat: int, seed: int = 0, max_elem: int = 25) -> FakeBatch:

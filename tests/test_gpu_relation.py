@@ -1,0 +1,117 @@
+"""GPU (-m gpu): cond = "relation" on the device -- the hand-derived SGD update kernel between the posterior and
+the draw (relation.cuh) against the oracle's restatement of logit_adjustment.update, which tests/test_oracle_relation.py pins
+to the reference's autograd implementation."""
+import pytest
+import torch
+
+from oracle import layoutdm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def synthetic_relation_cond(vo, B, seed, edge_p=0.3):
+    """cond dict of get_cond(..., "relation") (task.py:94-114) + a dense edge table shaped like AddRelationConstraints'
+    output (data/util.py:123-170: edges i < j, one size bit and one location bit each, UNKNOWN bits 0 / 4 otherwise)"""
+    g = torch.Generator().manual_seed(seed)
+    E = vo.n_elem
+    n_el = torch.randint(1, E + 1, (B,), generator=g)
+    n_el[0] = E
+    seq = torch.full((B, vo.S), vo.mask_id, dtype=torch.long)
+    mask = torch.zeros(B, vo.S, dtype=torch.bool)
+    adj = torch.zeros(B, E + 1, E + 1, dtype=torch.int32)
+    for b in range(B):
+        n = int(n_el[b])
+        seq[b, 0:5 * n:5] = torch.randint(0, vo.n_cat, (n,), generator=g)
+        mask[b, 0:5 * n:5] = True
+        seq[b, 5 * n:] = vo.pad_id
+        mask[b, 5 * n:] = True
+        for i in range(n + 1):
+            for j in range(i + 1, n + 1):
+                size = int(torch.randint(1, 4, (1,), generator=g)) if torch.rand(1, generator=g) < edge_p else 0
+                if torch.rand(1, generator=g) < edge_p:
+                    loc = [6, 9, 8][int(torch.randint(0, 3, (1,), generator=g))] if i == 0 else int(torch.randint(5, 10, (1,), generator=g))
+                else:
+                    loc = 4
+                m = (1 << size) | (1 << loc)
+                if m != (1 << 0 | 1 << 4):
+                    adj[b, i, j] = m
+    return dict(seq=seq, mask=mask, type="relation", rel_adj=adj)
+
+
+def engine(scale=2.0):
+    from layoutdm_b200 import Engine, Vocab
+    vo, spec = O.RICO25, O.ModelSpec()
+    sd = O.make_weights(vo, spec, seed=3, scale=scale)
+    return Engine.from_state_dict(sd, Vocab.for_dataset("rico25"), num_timesteps=spec.T), sd, vo, spec
+
+
+@pytest.mark.parametrize("lam,n_up,B", [(3e6, 3, 37), (1e4, 5, 8), (3e6, 1, 300)])
+def test_relation_update_kernel_matches_oracle(lam, n_up, B):
+    eng, sd, vo, spec = engine()
+    orc = O.Oracle(vo, spec, sd)
+    cond = synthetic_relation_cond(vo, B, seed=B)
+    cond.update(rel_lambda=lam, rel_num_update=n_up)
+    dcond = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in cond.items()}
+    g = torch.Generator().manual_seed(1)
+    for t in (70, 10, 9):
+        x_t = torch.where(torch.rand(B, vo.S, generator=g) < 0.4, torch.randint(0, vo.C - 2, (B, vo.S), generator=g), torch.full((B, vo.S), vo.mask_id))
+        x_t = torch.where(cond["mask"], cond["seq"], x_t)
+        logits = torch.randn(B, vo.S, vo.C, generator=g) * 3.0
+        want_lp = orc.logprob_from_logits(logits, x_t, t, cond, t_model=t)
+        base_lp = orc.logprob_from_logits(logits, x_t, t, {k: v for k, v in cond.items() if k != "rel_adj"}, t_model=t)
+        moved = (want_lp - base_lp).abs().max().item()
+        out, _, lp = eng.step(x_t.cuda(), t, t, {"name": "deterministic"}, dcond, want_logprob=True, logits_in=logits.cuda())
+        err = (lp.cpu() - want_lp).abs().max().item()
+        print(f"B={B} t={t} lambda={lam:g} x{n_up}: update moved log-probs by up to {moved:.3e}; |kernel - oracle| {err:.3e}")
+        if t >= 10:
+            assert moved > 1e-2, "inputs do not exercise the update"
+        assert err <= 1e-4 + 2e-5 * moved
+        want_ids = O.draw(want_lp, O.SamplingCfg(name="deterministic"))
+        diff = int((out.cpu() != want_ids).sum())
+        assert diff <= 0.001 * out.numel(), f"{diff} ids differ"     # argmax ties between saturated bins may break differently
+        assert torch.equal(out.cpu()[cond["mask"]], cond["seq"][cond["mask"]])
+
+
+def test_relation_batch_total_and_shard_invariance():
+    """the loss mean runs over the GLOBAL batch: a shard with rel_batch_total = B reproduces its rows of the full batch"""
+    eng, sd, vo, spec = engine()
+    B = 12
+    cond = synthetic_relation_cond(vo, B, seed=5)
+    cond.update(rel_lambda=3e5, rel_num_update=3)
+    g = torch.Generator().manual_seed(2)
+    logits = torch.randn(B, vo.S, vo.C, generator=g) * 3.0
+    x_t = cond["seq"].clone()
+    full = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in cond.items()}
+    _, _, lp = eng.step(x_t.cuda(), 50, 50, {"name": "deterministic"}, full, want_logprob=True, logits_in=logits.cuda())
+    part = {k: (v[6:].cuda() if isinstance(v, torch.Tensor) else v) for k, v in cond.items()}
+    part["rel_batch_total"] = B
+    _, _, lp2 = eng.step(x_t[6:].cuda(), 50, 50, {"name": "deterministic"}, part, want_logprob=True, logits_in=logits[6:].cuda())
+    assert torch.equal(lp[6:], lp2)
+
+
+def test_relation_sample_loop_stepwise_vs_oracle():
+    """the loop with the relation update inside (3 launches per step epilogue): every step on the kernel's own x_t agrees with
+    the same-rounding oracle step"""
+    eng, sd, vo, spec = engine()
+    orc = O.Oracle(vo, spec, sd, operand_dtype=torch.float16)
+    B = 6
+    cond = synthetic_relation_cond(vo, B, seed=9)
+    cond.update(rel_lambda=3e6, rel_num_update=3)
+    dcond = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in cond.items()}
+    plan = O.timestep_plan(spec.T, 10)
+    ids, trace = eng.sample_loop(B, plan, {"name": "random", "temperature": 1.0}, dcond, seed=4, trace=True)
+    ids2 = eng.sample_loop(B, plan, {"name": "random", "temperature": 1.0}, dcond, seed=4)
+    assert torch.equal(ids, ids2)
+    trace = trace.cpu()
+    x = cond["seq"].clone()
+    mism = 0
+    with torch.no_grad():
+        for i, (tm, tp) in enumerate(plan):
+            lp, _ = orc.step_logprob(x, tm, tp, cond)
+            want = O.draw(lp, O.SamplingCfg(name="random"), O.uniforms(4, i, 0, 0, B, vo.S, vo.C))
+            mism += int((want != trace[i]).sum())
+            x = trace[i]
+    print(f"relation loop: {mism} of {len(plan) * B * vo.S} ids differ from the oracle")
+    assert mism <= 0.01 * len(plan) * B * vo.S
+    assert torch.equal(ids.cpu()[cond["mask"]], cond["seq"][cond["mask"]])
+    assert (ids != vo.mask_id).all()
