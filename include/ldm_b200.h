@@ -148,6 +148,28 @@ int ldm_sample_host(LdmHandle* h, int32_t B, int32_t n_steps, const int32_t* t_m
 int ldm_q_sample(LdmHandle* h, int32_t B, const int64_t* x0_ids_dev, const int32_t* t_dev, uint64_t seed, int64_t b_global0,
                  int64_t* xt_ids_dev, void* stream);
 
+/* Training-side API on (B, S, C) log tensors with PER-LAYOUT timesteps t_dev[B] (SURVEY 8b "must keep working" / 8f-3).  Layout note:
+ * these tensors are token-major [B][S][C]; the reference's are (B, C, S) -- the Python mirror transposes.
+ *   ldm_predict_start : log p(x0 | x_t) = predict_start(log_onehot(xt), t)  (base.py:127-146: denoiser at per-layout timesteps,
+ *                       float64 log-softmax over the C-1 non-MASK classes, MASK = -70, clamp [-70, 0]); optional fp32 logits tap.
+ *   ldm_q_posterior   : q(x_{t-1} | x_t, x0~) for ANY log p(x0) (constrained.py:135-206, vanilla.py:112-151), x_t as ids.
+ *   ldm_q_pred        : log q(x_t | x0) for any log p(x0) (constrained.py:112-133 on each attribute's partial vocabulary,
+ *                       vanilla.py:90-110), t may be -1 (wraps to T); classes outside a token's vocabulary group = log(1e-30).
+ *   ldm_vb_terms      : what `forward` computes after x_t = q_sample(x0, t) (constrained.py:262-333, vanilla.py:177-243), forward
+ *                       only: per layout  kl = mean_s(multinomial_kl(log_true_prob, log_model_prob) * mask_weight),
+ *                       decoder_nll = mean_s(-log_categorical(log_onehot(x0), log_model_prob)),  kl_aux = mean_s(multinomial_kl(
+ *                       log_onehot(x0)[:-1], log_x0_recon[:-1]) * mask_weight); optional taps: log_model_prob [B][S][C] and the
+ *                       argmax ids of log_x0_recon / log_model_prob that feed the reference's accuracy book-keeping (:273-292). */
+int ldm_predict_start(LdmHandle* h, int32_t B, const int64_t* xt_ids_dev, const int32_t* t_dev, float* log_x0_out_dev,
+                      float* logits_out_dev, void* stream);
+int ldm_q_posterior(LdmHandle* h, int32_t B, const float* log_x_start_dev, const int64_t* xt_ids_dev, const int32_t* t_dev,
+                    float* log_prob_out_dev, void* stream);
+int ldm_q_pred(LdmHandle* h, int32_t B, const float* log_x_start_dev, const int32_t* t_dev, float* log_prob_out_dev, void* stream);
+int ldm_vb_terms(LdmHandle* h, int32_t B, const int64_t* x0_ids_dev, const int64_t* xt_ids_dev, const int32_t* t_dev,
+                 float mask_weight_mask, float mask_weight_other, float* kl_out_dev, float* decoder_nll_out_dev,
+                 float* kl_aux_out_dev, float* log_model_prob_out_dev, int64_t* x0_recon_ids_out_dev,
+                 int64_t* xtm1_recon_ids_out_dev, void* stream);
+
 /* ids -> layouts on the device == LayoutSequenceTokenizer.decode (layout_tokenizer.py:255-266) + BboxTokenizer.decode
  * (bbox_tokenizer.py:117-174).  centers_dev: [4][n_bins] cluster centres (kmeans / percentile) or NULL for linear bins.
  * Outputs (device): bbox [B][n_elem][4] f32 (xywh), label [B][n_elem] i64, mask [B][n_elem] u8 (1 = valid element). */

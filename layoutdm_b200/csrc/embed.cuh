@@ -45,7 +45,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, void* __restri
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 embed_adaln_kernel(const long long* __restrict__ ids /*[B][S]*/, const float* __restrict__ cat_emb /*[C][d]*/,
-                   const float* __restrict__ pos /*[S][d]*/, const float* __restrict__ adaln /*[2d] for (layer 0, t)*/,
+                   const float* __restrict__ pos /*[S][d]*/, const float* __restrict__ adaln_tab /*[T][2d] of layer 0*/, int t_model,
+                   const int* __restrict__ t_layout /*[n_layouts] per-layout timesteps (training-side calls) or nullptr*/,
                    float* __restrict__ x32 /*[B*128][d]*/, void* __restrict__ x16_, int n_layouts, int n_layouts_padded, int S, int d) {
   using O = OpT<BF16>;
   typename O::T* x16 = static_cast<typename O::T*>(x16_);
@@ -62,6 +63,7 @@ embed_adaln_kernel(const long long* __restrict__ ids /*[B][S]*/, const float* __
     return;
   }
   const long long id = ids[static_cast<size_t>(b) * S + s];
+  const float* adaln = adaln_tab + static_cast<size_t>(t_layout != nullptr ? __ldg(t_layout + b) : t_model) * 2 * d;
   const float4* e = reinterpret_cast<const float4*>(cat_emb + static_cast<size_t>(id) * d);
   const float4* p = reinterpret_cast<const float4*>(pos + static_cast<size_t>(s) * d);
   float4 v[4];

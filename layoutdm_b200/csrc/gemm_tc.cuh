@@ -59,6 +59,8 @@ struct GemmParams {
   // EPI_LN row statistics exchanged between the two CTA pairs that hold the two column tiles of a row block
   unsigned long long* ln_stats;   // [n_units * 2 CTAs][128 rows][2] {fp32 partial, launch epoch} words: sum and sum of squares over a unit's columns
   unsigned ln_epoch;
+  const int* t_layout;    // EPI_LN + adaln: per-layout timesteps (training-side calls): ln_scale then points at the layer's whole [T][2N]
+  int n_layouts;          //   AdaLN table and every (row block, CTA) = layout reloads its (scale, shift) row; nullptr: one timestep for all
   int tile_sched;         // 1: spread single (row block, N tile) tiles over the CTA pairs (small batches); 0: a pair walks all N tiles of a row block
   int dbg;                // bring-up probe (env LDM_GEMM_DEBUG), bit mask: 1 = skip the MMAs, 2 = skip the TMA operand loads, 4 = skip the epilogue body; results are garbage
 };
@@ -152,6 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int c = tile0 + i;
       const bool ok = c < p.N;
       sbias[i] = (ok && p.bias != nullptr) ? __ldg(p.bias + c) : 0.0f;
+      if (p.t_layout != nullptr) continue;                     // per-layout AdaLN rows are loaded per unit in the epilogue
       sbias[256 + i] = ok ? __ldg(p.ln_scale + c) + (p.adaln ? 1.0f : 0.0f) : 0.0f;
       sbias[512 + i] = ok ? __ldg(p.ln_shift + c) : 0.0f;
     }
@@ -381,6 +384,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int ce = (p.dbg & 4) ? c_begin : (half == 0 ? kSplit : kFull + n_blk);   // tile 1 has one more (half-valid) chunk
         const uint32_t taddr = tmem_base + tlane + acc * kAccStride;
         float sum = 0.0f, sq = 0.0f;
+        if (p.t_layout != nullptr) {
+          // per-layout timesteps: this CTA's layout (= its 128-row block) picks its own AdaLN (scale, shift) row.  Phase B of the
+          // previous unit must be through with gamma / beta before they are replaced; phase A does not read them and the
+          // statistics barrier below orders the new values before phase B.
+          named_bar_sync(1, kEpiThreads);
+          const int tl = m_blk < p.n_layouts ? __ldg(p.t_layout + m_blk) : 0;
+          const float* tab = p.ln_scale + static_cast<size_t>(tl) * 2 * p.N;
+          const int i = static_cast<int>(threadIdx.x) - 64, c = n0 + i;
+          const bool ok = c < p.N;
+          sbias[256 + i] = ok ? __ldg(tab + c) + 1.0f : 0.0f;
+          sbias[512 + i] = ok ? __ldg(tab + p.N + c) : 0.0f;
+        }
         // ---------------- phase A ----------------
         {
           auto issue_resid = [&](int c) {                     // async: 32 rows x 32 fp32 of the residual -> buffer (c - c_begin) % n_lbuf

@@ -338,7 +338,7 @@ int ensure_workspace(LdmHandle* h, int n_layouts) {
 }
 
 template <bool BF16>
-int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, cudaStream_t st) {
+int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, cudaStream_t st, const int* t_layout = nullptr) {
   const int d = h->desc.d_model, ff = h->desc.d_ff, L = h->L, T = h->T;
   const int np = (n + 1) & ~1;            // layouts incl. the padding layout of an odd batch
   const int M = np * kBM;
@@ -356,7 +356,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     const int warps = np * 128, blocks = (warps * 32 + 255) / 256;
     ProfScope ps(h, CAT_EMBED, st);
     CK(launch_step(h, embed_adaln_kernel<BF16>, blocks, 256, 0, st, false, ids_in, (const float*)h->cat_emb, (const float*)h->pos,
-                   (const float*)(h->adaln + (static_cast<size_t>(0) * T + t_model) * 2 * d), h->x32, h->x16, n, np, h->S, d));
+                   (const float*)h->adaln, t_model, t_layout, h->x32, h->x16, n, np, h->S, d));
   }
   LDM_STAGE_DONE();
   for (int l = 0; l < L; ++l) {
@@ -396,6 +396,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       if (l + 1 < L) {
         const float* tab = h->adaln + (static_cast<size_t>(l + 1) * T + t_model) * 2 * d;
         p.ln_scale = tab; p.ln_shift = tab + d; p.adaln = 1; p.out32 = h->x32; p.out = h->x16; mo = &h->b_x16;
+        if (t_layout) { p.ln_scale = h->adaln + static_cast<size_t>(l + 1) * T * 2 * d; p.t_layout = t_layout; p.n_layouts = n; }   // per-layout rows
       } else {
         p.ln_scale = h->hlnw; p.ln_shift = h->hlnb; p.adaln = 0; p.out32 = nullptr; p.out = h->z16;
       }
@@ -899,6 +900,95 @@ int ldm_make_cond(LdmHandle* h, int32_t B, int32_t cond_type, const int64_t* lab
                                                      h->desc.n_elem, h->desc.n_cat, h->desc.n_bins, h->C - 2, h->C - 1, cond_type,
                                                      static_cast<float>(dd), static_cast<float>(1.0 - dd));
   }
+  CK(cudaGetLastError());
+  return LDM_OK;
+}
+
+namespace {
+
+StepParams base_step_params(const LdmHandle* h, int B) {
+  StepParams p{};
+  p.n_layouts = B; p.S = h->S; p.C = h->C; p.n_attr = h->desc.n_attr;
+  p.pad_id = h->C - 2; p.mask_id = h->C - 1;
+  p.constrained = h->desc.q_type == 0;
+  for (int g = 0; g < h->desc.n_attr && g < kMaxAttr; ++g) {
+    p.grp_start[g] = g == 0 ? 0 : h->desc.n_cat + (g - 1) * h->desc.n_bins;
+    p.grp_n[g] = g == 0 ? h->desc.n_cat : h->desc.n_bins;
+  }
+  p.T = h->T; p.sched = h->sched; p.lae = h->lae;
+  p.logits = h->logits; p.ld_logits = kLogitLd;
+  p.mode = SAMP_DETERMINISTIC; p.temperature = 1.0f;
+  return p;
+}
+
+int run_denoiser_per_layout_t(LdmHandle* h, int B, const long long* ids, const int32_t* t_dev, cudaStream_t st) {
+  int rc = ensure_workspace(h, B);
+  if (rc) return rc;
+  return h->bf16 ? launch_denoiser<true>(h, B, ids, 0, st, t_dev) : launch_denoiser<false>(h, B, ids, 0, st, t_dev);
+}
+
+}  // namespace
+
+int ldm_predict_start(LdmHandle* h, int32_t B, const int64_t* xt_ids, const int32_t* t_dev, float* log_x0_out, float* logits_out, void* stream) {
+  if (!h || !xt_ids || !t_dev || !log_x0_out || B <= 0) return fail(LDM_ERR_INVALID, "bad ldm_predict_start arguments");
+  CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = run_denoiser_per_layout_t(h, B, reinterpret_cast<const long long*>(xt_ids), t_dev, st);
+  if (rc) return rc;
+  if (logits_out) { ProfScope ps(h, CAT_MISC, st); logits_gather_kernel<<<1024, 256, 0, st>>>(h->logits, logits_out, B, h->S, h->C); }
+  StepParams p = base_step_params(h, B);
+  p.ids_in = reinterpret_cast<const long long*>(xt_ids); p.t_layout = t_dev; p.lx0_out = log_x0_out;   // ids_out == nullptr: no draw
+  const int blocks = (B * h->S * 32 + 255) / 256;
+  { ProfScope ps(h, CAT_EPILOGUE, st); CK(launch_step(h, posterior_sample_kernel, blocks, 256, 0, st, false, p)); }
+  CK(cudaGetLastError());
+  return LDM_OK;
+}
+
+int ldm_q_posterior(LdmHandle* h, int32_t B, const float* log_x_start, const int64_t* xt_ids, const int32_t* t_dev, float* out, void* stream) {
+  if (!h || !log_x_start || !xt_ids || !t_dev || !out || B <= 0) return fail(LDM_ERR_INVALID, "bad ldm_q_posterior arguments");
+  CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StepParams p = base_step_params(h, B);
+  p.ids_in = reinterpret_cast<const long long*>(xt_ids); p.t_layout = t_dev; p.lx0_in = log_x_start; p.logprob_out = out;
+  const int blocks = (B * h->S * 32 + 255) / 256;
+  { ProfScope ps(h, CAT_EPILOGUE, st); CK(launch_step(h, posterior_sample_kernel, blocks, 256, 0, st, false, p)); }
+  CK(cudaGetLastError());
+  return LDM_OK;
+}
+
+int ldm_q_pred(LdmHandle* h, int32_t B, const float* log_x_start, const int32_t* t_dev, float* out, void* stream) {
+  if (!h || !log_x_start || !t_dev || !out || B <= 0) return fail(LDM_ERR_INVALID, "bad ldm_q_pred arguments");
+  CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StepParams p = base_step_params(h, B);
+  p.t_layout = t_dev;
+  { ProfScope ps(h, CAT_MISC, st); q_pred_kernel<<<1024, 256, 0, st>>>(p, log_x_start, out); }
+  CK(cudaGetLastError());
+  return LDM_OK;
+}
+
+int ldm_vb_terms(LdmHandle* h, int32_t B, const int64_t* x0_ids, const int64_t* xt_ids, const int32_t* t_dev, float mask_weight_mask,
+                 float mask_weight_other, float* kl_out, float* nll_out, float* kl_aux_out, float* log_model_prob_out,
+                 int64_t* x0_recon_out, int64_t* xtm1_recon_out, void* stream) {
+  if (!h || !x0_ids || !xt_ids || !t_dev || !kl_out || !nll_out || B <= 0) return fail(LDM_ERR_INVALID, "bad ldm_vb_terms arguments");
+  CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = run_denoiser_per_layout_t(h, B, reinterpret_cast<const long long*>(xt_ids), t_dev, st);
+  if (rc) return rc;
+  // per-token terms live in the (free at this point) fp32 residual buffer of the workspace: 3 x [B][S] floats
+  float* tok = h->y32;
+  const size_t nt = static_cast<size_t>(B) * h->S;
+  VbParams v{};
+  v.sp = base_step_params(h, B);
+  v.sp.ids_in = reinterpret_cast<const long long*>(xt_ids); v.sp.t_layout = t_dev; v.sp.logprob_out = log_model_prob_out;
+  v.x0 = reinterpret_cast<const long long*>(x0_ids); v.w_mask = mask_weight_mask; v.w_other = mask_weight_other;
+  v.kl_tok = tok; v.nll_tok = tok + nt; v.aux_tok = kl_aux_out ? tok + 2 * nt : nullptr;
+  v.x0_recon = reinterpret_cast<long long*>(x0_recon_out); v.xtm1_recon = reinterpret_cast<long long*>(xtm1_recon_out);
+  const int blocks = (B * h->S * 32 + 255) / 256, rblocks = (B * 32 + 255) / 256;
+  { ProfScope ps(h, CAT_EPILOGUE, st); CK(launch_step(h, vb_terms_kernel, blocks, 256, 0, st, false, v)); }
+  { ProfScope ps(h, CAT_MISC, st); CK(launch_step(h, row_mean_kernel, rblocks, 256, 0, st, false, (const float*)v.kl_tok, kl_out, B, h->S)); }
+  { ProfScope ps(h, CAT_MISC, st); CK(launch_step(h, row_mean_kernel, rblocks, 256, 0, st, false, (const float*)v.nll_tok, nll_out, B, h->S)); }
+  if (kl_aux_out) { ProfScope ps(h, CAT_MISC, st); CK(launch_step(h, row_mean_kernel, rblocks, 256, 0, st, false, (const float*)v.aux_tok, kl_aux_out, B, h->S)); }
   CK(cudaGetLastError());
   return LDM_OK;
 }

@@ -25,6 +25,10 @@ struct StepParams {
   const float* lae;                      // [G][T+1][4] log_add_exp terms that depend on (group, t) only (lae_table_kernel)
   const float* logits; int ld_logits;    // [n_layouts*128][ld]; row = b*128 + s      (nullptr if logprob_in)
   const float* logprob_in;               // [n_layouts][S][C] or nullptr: draw from given log-probs (relation hook)
+  const float* lx0_in;                   // [n_layouts][S][C] or nullptr: log p(x0) given by the caller instead of predict_start(logits)
+                                         // (q_posterior as a callable API, constrained.py:135-206; the MASK column is ignored like :191)
+  float* lx0_out;                        // [n_layouts][S][C] or nullptr: tap of predict_start's output (base.py:127-146)
+  const int* t_layout;                   // [n_layouts] or nullptr: per-layout posterior timestep (training-side calls) instead of t_post
   const long long* ids_in;               // [n_layouts][S]
   const long long* cond_seq; const unsigned char* cond_mask; const long long* cond_seq_orig; const float* refine_tbl;
   int cond_flags;
@@ -57,6 +61,84 @@ __global__ void lae_table_kernel(const float* __restrict__ sched, float* __restr
   reinterpret_cast<float4*>(lae)[i] = o;
 }
 
+// predict_start (base.py:127-146) for one token: float64 log-softmax over the C-1 non-MASK classes, MASK = -70, clamp [-70, 0].
+// Class ownership: lane l holds classes 4l..4l+3 and 128+l.
+LDM_DEVINL void predict_start_token(const StepParams& p, const float* lrow, const int lane, const int (&cls)[5], const bool (&valid)[5], float (&lx0)[5]) {
+  const int C = p.C;
+  float l[5];
+  {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(lrow) + lane);
+    l[0] = v.x; l[1] = v.y; l[2] = v.z; l[3] = v.w;
+    l[4] = valid[4] ? __ldg(lrow + cls[4]) : 0.0f;
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) if (valid[j] && cls[j] < C - 1) mx = fmaxf(mx, l[j]);
+  mx = warp_max(mx);
+  double dsum = 0.0;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) if (valid[j] && cls[j] < C - 1) dsum += exp(static_cast<double>(l[j]) - static_cast<double>(mx));
+  dsum = warp_sum_d(dsum);
+  const double lse = static_cast<double>(mx) + log(dsum);
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const float v = (cls[j] < C - 1) ? static_cast<float>(static_cast<double>(l[j]) - lse) : -70.0f;
+    lx0[j] = fminf(fmaxf(v, -70.0f), 0.0f);
+  }
+}
+
+// q(x_{t-1} | x_t, x0~) in log space for one token, every class (constrained.py:135-206 / vanilla.py:112-151): lx0 = log p(x0)
+// (its MASK entry is not used), x_t the token's current id, t the posterior timestep; classes outside the token's vocabulary
+// group come out as log(1e-30) (Converter.p_to_f_log), invalid lanes as -inf.
+LDM_DEVINL void posterior_token_logprob(const StepParams& p, const int s, const int x_t, const int t, const float (&lx0)[5],
+                                        const int (&cls)[5], const bool (&valid)[5], float (&lp)[5]) {
+  const int g = p.constrained ? (s % p.n_attr) : 0;
+  const int gst = p.grp_start[g], gn = p.grp_n[g];
+  const float* tab = p.sched + static_cast<size_t>(g) * 8 * (p.T + 1);
+  const int tm1 = (t - 1 + (p.T + 1)) % (p.T + 1);
+  const int TT = p.T + 1;
+  const float lat = tab[0 * TT + t], lbt = tab[1 * TT + t], lct = tab[2 * TT + t];
+  const float lcat = tab[3 * TT + t], lcbt = tab[4 * TT + t], lcct = tab[5 * TT + t];
+  const float lcat1 = tab[3 * TT + tm1], lcbt1 = tab[4 * TT + tm1], lcct1 = tab[5 * TT + tm1], l1mcct1 = tab[7 * TT + tm1];
+  const bool is_mask = (x_t == p.mask_id);
+
+  bool in_grp[5]; float q[5], one[5];
+  float qmax = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int c = cls[j];
+    in_grp[j] = valid[j] && (p.constrained ? ((c >= gst && c < gst + gn) || c == p.pad_id || c == p.mask_id) : true);
+    q[j] = -INFINITY; one[j] = 0.0f;
+    if (in_grp[j]) {
+      if (c != p.mask_id) {
+        const float v = (c == x_t) ? 0.0f : kLogEps;
+        const float lq = is_mask ? lcct : log_add_exp(v + lcat, lcbt);
+        one[j] = is_mask ? lct : log_add_exp(v + lat, lbt);
+        q[j] = lx0[j] - lq;
+      } else {
+        q[j] = kLogEps;
+        one[j] = is_mask ? 0.0f : kLogEps;
+      }
+      qmax = fmaxf(qmax, q[j]);
+    }
+  }
+  qmax = warp_max(qmax);
+  float qs = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) if (in_grp[j]) qs += expf(q[j] - qmax);
+  const float L = logf(warp_sum(qs)) + qmax;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    if (in_grp[j]) {
+      const float qn = q[j] - L;
+      const float ev = (cls[j] != p.mask_id) ? log_add_exp(qn + lcat1, lcbt1) : log_add_exp(qn + l1mcct1, lcct1);
+      lp[j] = fminf(fmaxf((ev + one[j]) + L, -70.0f), 0.0f);
+    } else {
+      lp[j] = valid[j] ? kLogEps : -INFINITY;
+    }
+  }
+}
+
 // One token, every class (lane l: classes 4l..4l+3 and 128+l): any q_type, any sampling mode, log-prob in / out.
 LDM_DEVINL void posterior_token_generic(const StepParams& p, const int token, const int lane) {
   const int b = token / p.S, s = token % p.S;
@@ -79,76 +161,18 @@ LDM_DEVINL void posterior_token_generic(const StepParams& p, const int token, co
       for (int j = 0; j < 5; ++j) if (valid[j] && cls[j] == p.pad_id) lp[j] = kLogEps;
     }
   } else {
-    // ---- predict_start: float64 log-softmax over the C-1 non-MASK classes, clamp [-70, 0] ----
-    const float* lrow = p.logits + (static_cast<size_t>(b) * 128 + s) * p.ld_logits;
-    float l[5];
-    {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(lrow) + lane);
-      l[0] = v.x; l[1] = v.y; l[2] = v.z; l[3] = v.w;
-      l[4] = valid[4] ? __ldg(lrow + cls[4]) : 0.0f;
-    }
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) if (valid[j] && cls[j] < C - 1) mx = fmaxf(mx, l[j]);
-    mx = warp_max(mx);
-    double dsum = 0.0;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) if (valid[j] && cls[j] < C - 1) dsum += exp(static_cast<double>(l[j]) - static_cast<double>(mx));
-    dsum = warp_sum_d(dsum);
-    const double lse = static_cast<double>(mx) + log(dsum);
     float lx0[5];
+    if (p.lx0_in != nullptr) {
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const float v = (cls[j] < C - 1) ? static_cast<float>(static_cast<double>(l[j]) - lse) : -70.0f;
-      lx0[j] = fminf(fmaxf(v, -70.0f), 0.0f);
+      for (int j = 0; j < 5; ++j) lx0[j] = valid[j] ? p.lx0_in[static_cast<size_t>(token) * C + cls[j]] : -70.0f;
+    } else {
+      predict_start_token(p, p.logits + (static_cast<size_t>(b) * 128 + s) * p.ld_logits, lane, cls, valid, lx0);
     }
-
-    // ---- posterior q(x_{t-1} | x_t, x0~) in log space ----
-    const int g = p.constrained ? (s % p.n_attr) : 0;
-    const int gst = p.grp_start[g], gn = p.grp_n[g];
-    const float* tab = p.sched + static_cast<size_t>(g) * 8 * (p.T + 1);
-    const int t = p.t_post, tm1 = (t - 1 + (p.T + 1)) % (p.T + 1);
-    const int TT = p.T + 1;
-    const float lat = tab[0 * TT + t], lbt = tab[1 * TT + t], lct = tab[2 * TT + t];
-    const float lcat = tab[3 * TT + t], lcbt = tab[4 * TT + t], lcct = tab[5 * TT + t];
-    const float lcat1 = tab[3 * TT + tm1], lcbt1 = tab[4 * TT + tm1], lcct1 = tab[5 * TT + tm1], l1mcct1 = tab[7 * TT + tm1];
-    const bool is_mask = (x_t == p.mask_id);
-
-    bool in_grp[5]; float q[5], one[5];
-    float qmax = -INFINITY;
+    if (p.lx0_out != nullptr) {
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const int c = cls[j];
-      in_grp[j] = valid[j] && (p.constrained ? ((c >= gst && c < gst + gn) || c == p.pad_id || c == p.mask_id) : true);
-      q[j] = -INFINITY; one[j] = 0.0f;
-      if (in_grp[j]) {
-        if (c != p.mask_id) {
-          const float v = (c == x_t) ? 0.0f : kLogEps;
-          const float lq = is_mask ? lcct : log_add_exp(v + lcat, lcbt);
-          one[j] = is_mask ? lct : log_add_exp(v + lat, lbt);
-          q[j] = lx0[j] - lq;
-        } else {
-          q[j] = kLogEps;
-          one[j] = is_mask ? 0.0f : kLogEps;
-        }
-        qmax = fmaxf(qmax, q[j]);
-      }
+      for (int j = 0; j < 5; ++j) if (valid[j]) p.lx0_out[static_cast<size_t>(token) * C + cls[j]] = lx0[j];
     }
-    qmax = warp_max(qmax);
-    float qs = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) if (in_grp[j]) qs += expf(q[j] - qmax);
-    const float L = logf(warp_sum(qs)) + qmax;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      if (in_grp[j]) {
-        const float qn = q[j] - L;
-        const float ev = (cls[j] != p.mask_id) ? log_add_exp(qn + lcat1, lcbt1) : log_add_exp(qn + l1mcct1, lcct1);
-        lp[j] = fminf(fmaxf((ev + one[j]) + L, -70.0f), 0.0f);
-      } else {
-        lp[j] = valid[j] ? kLogEps : -INFINITY;
-      }
-    }
+    posterior_token_logprob(p, s, x_t, p.t_layout ? __ldg(p.t_layout + b) : p.t_post, lx0, cls, valid, lp);
 
     // ---- conditioning adjustments, in the reference's order ----
     if (p.cond_flags) {
@@ -174,6 +198,7 @@ LDM_DEVINL void posterior_token_generic(const StepParams& p, const int token, co
 #pragma unroll
     for (int j = 0; j < 5; ++j) if (valid[j]) p.logprob_out[static_cast<size_t>(token) * C + cls[j]] = lp[j];
   }
+  if (p.ids_out == nullptr) return;        // log-probabilities only (q_posterior / predict_start as callable APIs)
 
   // ---- draw ----
   float score[5];
@@ -493,6 +518,113 @@ __global__ void __launch_bounds__(256) posterior_sample_group_kernel(const StepP
     if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
   }
   if (lane == 0) p.ids_out[token] = best_c;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Training-side terms of the variational bound, per token: what `forward` computes after x_t has been drawn
+// (T/models/categorical_diffusion/constrained.py:262-333, vanilla.py:177-243):
+//   log_x0_recon   = predict_start(x_t, t)                       (logits of the denoiser run at per-layout timesteps)
+//   log_model_prob = q_posterior(log_x0_recon, x_t, t)           log_true_prob = q_posterior(log_onehot(x0), x_t, t)
+//   kl   = sum_c exp(true)(true - model) * mask_weight           util.py multinomial_kl, constrained.py:295-302
+//   nll  = -sum_c exp(log_onehot(x0)) * model                    log_categorical, :304
+//   aux  = sum_{c != MASK} exp(log_onehot(x0)) (log_onehot(x0) - log_x0_recon) * mask_weight     :321-325
+// plus the argmax ids the reference's accuracy book-keeping uses (:273-292).  One warp per token, forward only.
+struct VbParams {
+  StepParams sp;                         // logits / ids_in (= x_t) / t_layout / schedule / optional logprob_out (= log_model_prob)
+  const long long* x0;                   // [n_layouts][S]
+  float w_mask, w_other;                 // mask_weight[0] (x_t == MASK), mask_weight[1]
+  float* kl_tok; float* nll_tok; float* aux_tok;   // [n_layouts][S]; aux_tok may be nullptr
+  long long* x0_recon; long long* xtm1_recon;      // [n_layouts][S] or nullptr
+};
+
+LDM_DEVINL int warp_argmax_first(float v[5], const int (&cls)[5], const bool (&valid)[5]) {
+  float best = -INFINITY; int best_c = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) if (valid[j] && (v[j] > best || (v[j] == best && cls[j] < best_c))) { best = v[j]; best_c = cls[j]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+    if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+  }
+  return best_c;
+}
+
+__global__ void __launch_bounds__(256) vb_terms_kernel(const VbParams v) {
+  const StepParams& p = v.sp;
+  const int token = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (token >= p.n_layouts * p.S) return;
+  pdl_sync();
+  const int b = token / p.S, s = token % p.S;
+  const int C = p.C;
+  int cls[5]; bool valid[5];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { cls[j] = 4 * lane + j; valid[j] = cls[j] < C; }
+  cls[4] = 128 + lane; valid[4] = cls[4] < C;
+  const int x_t = static_cast<int>(p.ids_in[token]);
+  const int x0 = static_cast<int>(v.x0[token]);
+  const int t = __ldg(p.t_layout + b);
+  float lx0[5], lmp[5], lxs[5], ltp[5];
+  predict_start_token(p, p.logits + (static_cast<size_t>(b) * 128 + s) * p.ld_logits, lane, cls, valid, lx0);
+  posterior_token_logprob(p, s, x_t, t, lx0, cls, valid, lmp);
+#pragma unroll
+  for (int j = 0; j < 5; ++j) lxs[j] = (cls[j] == x0) ? 0.0f : kLogEps;            // index_to_log_onehot (util.py:34-40)
+  posterior_token_logprob(p, s, x_t, t, lxs, cls, valid, ltp);
+  float kl = 0.0f, nll = 0.0f, aux = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    if (valid[j]) {
+      kl += expf(ltp[j]) * (ltp[j] - lmp[j]);
+      nll += expf(lxs[j]) * lmp[j];
+      if (cls[j] < C - 1) aux += expf(lxs[j]) * (lxs[j] - lx0[j]);
+    }
+  }
+  kl = warp_sum(kl); nll = -warp_sum(nll); aux = warp_sum(aux);
+  const float w = (x_t == p.mask_id) ? v.w_mask : v.w_other;
+  if (p.logprob_out != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) if (valid[j]) p.logprob_out[static_cast<size_t>(token) * C + cls[j]] = lmp[j];
+  }
+  const int a0 = v.x0_recon ? warp_argmax_first(lx0, cls, valid) : 0;
+  const int a1 = v.xtm1_recon ? warp_argmax_first(lmp, cls, valid) : 0;
+  if (lane == 0) {
+    v.kl_tok[token] = kl * w; v.nll_tok[token] = nll;
+    if (v.aux_tok) v.aux_tok[token] = aux * w;
+    if (v.x0_recon) v.x0_recon[token] = a0;
+    if (v.xtm1_recon) v.xtm1_recon[token] = a1;
+  }
+}
+
+// mean over the S tokens of every layout (mean_except_batch, util.py:11-12): one warp per layout, fixed summation order
+__global__ void row_mean_kernel(const float* __restrict__ in, float* __restrict__ out, int n_rows, int S) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  pdl_sync();
+  float acc = 0.0f;
+  for (int i = lane; i < S; i += 32) acc += in[static_cast<size_t>(row) * S + i];
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc / static_cast<float>(S);
+}
+
+// q_pred on full-vocabulary (n_layouts, S, C) log tensors: log q(x_t | x_0) for arbitrary log p(x_0) (constrained.py:112-133 per
+// attribute on the partial vocabularies, vanilla.py:90-110); classes outside the token's group stay at log(1e-30) like
+// Converter.p_to_f_log fills them.  t may be -1 (wraps to T, :115).
+__global__ void q_pred_kernel(const StepParams p, const float* __restrict__ lx, float* __restrict__ out) {
+  const size_t n = static_cast<size_t>(p.n_layouts) * p.S * p.C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % p.C); const size_t tok = i / p.C; const int s = static_cast<int>(tok % p.S); const int b = static_cast<int>(tok / p.S);
+    const int g = p.constrained ? (s % p.n_attr) : 0;
+    const int gst = p.grp_start[g], gn = p.grp_n[g];
+    const bool in_grp = p.constrained ? ((c >= gst && c < gst + gn) || c == p.pad_id || c == p.mask_id) : true;
+    float r = kLogEps;
+    if (in_grp) {
+      const int TT = p.T + 1;
+      const int t = (__ldg(p.t_layout + b) + TT) % TT;
+      const float* tab = p.sched + static_cast<size_t>(g) * 8 * TT;
+      r = (c != p.mask_id) ? log_add_exp(lx[i] + tab[3 * TT + t], tab[4 * TT + t]) : log_add_exp(lx[i] + tab[7 * TT + t], tab[5 * TT + t]);
+    }
+    out[i] = r;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from .engine import Engine, sampling_struct
-from .vocab import Vocab, decode_ids, linear_centers, refinement_table, relation_edge_table, timestep_plan
+from .vocab import Vocab, decode_ids, group_full_ids, linear_centers, refinement_table, relation_edge_table, timestep_plan
 
 
 def _cfg_get(cfg, key, default=None):
@@ -172,6 +172,108 @@ class FusedMaskAndReplaceDiffusion:
         out = self._step_ids(ids, t_model, t_post, sampling_cfg, cond_d, self._seed, self._step_ctr)
         self._step_ctr += 1
         return index_to_log_onehot(out, self.num_classes)
+
+    # ---- training-side API ("signatures that must keep working"; forward only, no autograd) -----------------
+    VAR_NAMES = ("c", "x", "y", "w", "h")
+
+    def _key_index(self, key: str) -> int:
+        return self.VAR_NAMES.index(key) if self.engine.q_type == "constrained" else 0
+
+    def predict_start(self, log_x_t: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """base.py:127-146: log_x_t (B,C,S) log one-hot, t (B,) -> log p(x0|xt) (B,C,S)"""
+        return self.engine.predict_start(log_x_t.argmax(1), t).permute(0, 2, 1).contiguous()
+
+    def q_posterior(self, log_x_start: torch.Tensor, log_x_t: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """constrained.py:135-206 / vanilla.py:112-151: (B,C,S) log p(x0), (B,C,S) log one-hot x_t, t (B,) -> (B,C,S)"""
+        assert t.min().item() >= 0 and t.max().item() < self.num_timesteps
+        out = self.engine.q_posterior(log_x_start.permute(0, 2, 1), log_x_t.argmax(1), t)
+        return out.permute(0, 2, 1).contiguous()
+
+    def q_pred(self, log_x_start: torch.Tensor, t: torch.Tensor, key: Optional[str] = None) -> torch.Tensor:
+        """constrained.py:112-133: log q(x_t|x_0) on attribute `key`'s PARTIAL vocabulary, log_x_start (B, K_key, S/5) -> same shape;
+        vanilla (key=None): (B,C,S) -> (B,C,S)  (vanilla.py:90-110)"""
+        v = self.vocab
+        if self.engine.q_type != "constrained" or key is None:
+            return self.engine.q_pred(log_x_start.permute(0, 2, 1), t).permute(0, 2, 1).contiguous()
+        g = self._key_index(key)
+        ids = torch.tensor(group_full_ids(v, g), device=self.device)
+        B, K, Sg = log_x_start.shape
+        assert K == ids.numel() and Sg == v.n_elem
+        full = torch.full((B, v.S, v.C), -69.07755278982137, device=self.device)
+        full[:, g::v.n_attr, ids] = log_x_start.to(self.device).permute(0, 2, 1)
+        out = self.engine.q_pred(full, t)
+        return out[:, g::v.n_attr][..., ids].permute(0, 2, 1).contiguous()
+
+    def q_sample(self, log_x_start: torch.Tensor, t: torch.Tensor, key: Optional[str] = None, seed: Optional[int] = None) -> torch.Tensor:
+        """constrained.py:223-230: x_t ~ q(x_t|x_0) for attribute `key` (log one-hot in, log one-hot out, partial vocabulary)"""
+        v = self.vocab
+        seed = self._new_seed() if seed is None else seed
+        if self.engine.q_type != "constrained" or key is None:
+            xt = self.engine.q_sample(log_x_start.argmax(1), t, seed)
+            return index_to_log_onehot(xt, v.C)
+        g = self._key_index(key)
+        ids = torch.tensor(group_full_ids(v, g), device=self.device)
+        x0 = torch.full((log_x_start.shape[0], v.S), v.pad_id, dtype=torch.long, device=self.device)
+        x0[:, g::v.n_attr] = ids[log_x_start.to(self.device).argmax(1)]
+        xt = self.engine.q_sample(x0, t, seed)[:, g::v.n_attr]
+        part = (xt[..., None] == ids).long().argmax(-1)                     # full id -> index in the partial vocabulary
+        return index_to_log_onehot(part, ids.numel())
+
+    def sample_time(self, b: int, device=None, method: str = "uniform"):
+        """base.py:179-203 (host-side importance sampling over the running loss history)"""
+        device = self.device if device is None else device
+        if method == "importance":
+            if not (self.Lt_count > 10).all():
+                return self.sample_time(b, device, method="uniform")
+            Lt_sqrt = torch.sqrt(self.Lt_history + 1e-10) + 0.0001
+            Lt_sqrt[0] = Lt_sqrt[1]
+            pt_all = Lt_sqrt / Lt_sqrt.sum()
+            t = torch.multinomial(pt_all, num_samples=b, replacement=True)
+            return t, pt_all.gather(dim=0, index=t)
+        if method == "uniform":
+            t = torch.randint(0, self.num_timesteps, (b,), device=device).long()
+            return t, torch.ones_like(t).float() / self.num_timesteps
+        raise ValueError
+
+    def forward(self, x: torch.Tensor, is_train: bool = True, t: Optional[torch.Tensor] = None, pt: Optional[torch.Tensor] = None,
+                seed: Optional[int] = None):
+        """constrained.py:232-333 / vanilla.py:177-243, FORWARD ONLY (validation loss; no autograd graph is built -- the optimiser
+        step of the reference's training loop stays out of scope).  x (B,S) ids -> ({"probs": (B,C,S)}, {"kl_loss", "aux_loss"})."""
+        if not hasattr(self, "Lt_history"):
+            self.Lt_history = torch.zeros(self.num_timesteps, device=self.device)
+            self.Lt_count = torch.zeros(self.num_timesteps, device=self.device)
+            self.diffusion_acc_list = [0] * self.num_timesteps
+            self.diffusion_keep_list = [0] * self.num_timesteps
+            self.mask_weight = [1.0, 1.0]
+            self.auxiliary_loss_weight = 1e-1
+            self.adaptive_auxiliary_loss = True
+        x = x.to(self.device)
+        b = x.size(0)
+        if t is None:
+            t, pt = self.sample_time(b, self.device, "importance")
+        t, pt = t.to(self.device), pt.to(self.device)
+        xt = self.engine.q_sample(x, t, self._new_seed() if seed is None else seed)
+        aux_on = self.auxiliary_loss_weight != 0 and is_train
+        r = self.engine.vb_terms(x, xt, t, self.mask_weight, want_aux=aux_on, want_log_model_prob=True, want_recon_ids=True)
+        same0 = (r["x0_recon"] == x).float().mean(1).cpu()
+        same1 = (r["xt_1_recon"] == xt).float().mean(1).cpu()
+        for i, this_t in enumerate(t.tolist()):                                               # :273-292
+            self.diffusion_acc_list[this_t] = same0[i].item() * 0.1 + self.diffusion_acc_list[this_t] * 0.9
+            self.diffusion_keep_list[this_t] = same1[i].item() * 0.1 + self.diffusion_keep_list[this_t] * 0.9
+        mask = (t == 0).float()
+        kl_loss = mask * r["decoder_nll"] + (1.0 - mask) * r["kl"]                             # :307-308
+        Lt2 = kl_loss.pow(2)
+        Lt2_prev = self.Lt_history.gather(dim=0, index=t)
+        self.Lt_history.scatter_(dim=0, index=t, src=(0.1 * Lt2 + 0.9 * Lt2_prev))
+        self.Lt_count.scatter_add_(dim=0, index=t, src=torch.ones_like(Lt2))
+        losses = {"kl_loss": (kl_loss / pt).mean()}
+        if aux_on:
+            kl_aux_loss = mask * r["decoder_nll"] + (1.0 - mask) * r["kl_aux"]
+            w = (1 - t / self.num_timesteps) + 1.0 if self.adaptive_auxiliary_loss else 1.0
+            losses["aux_loss"] = (w * self.auxiliary_loss_weight * kl_aux_loss / pt).mean()
+        return {"probs": r["log_model_prob"].permute(0, 2, 1).exp()}, losses
+
+    __call__ = forward
 
     def q_sample_ids(self, x0: torch.Tensor, t: torch.Tensor, seed: Optional[int] = None) -> torch.Tensor:
         """corruption x_t ~ q(x_t | x_0) on ids (constrained.py:223-230 applied per attribute as in :232-260)"""

@@ -218,6 +218,58 @@ class Engine:
         _lib.check(self.lib.ldm_q_sample(self._h, B, _ptr(x0), _ptr(t32), C.c_uint64(seed), C.c_int64(b_global0), _ptr(out), self._stream()))
         return out
 
+    # ---- training-side API on (B, S, C) log tensors, per-layout timesteps ------------------------------
+    def _t32(self, t: torch.Tensor, B: int, lo: int = 0) -> torch.Tensor:
+        t = t.to(self.device).view(-1)
+        assert t.numel() == B and int(t.min()) >= lo and int(t.max()) < self.T                     # constrained.py:139
+        return t.to(torch.int32).contiguous()
+
+    def predict_start(self, xt: torch.Tensor, t: torch.Tensor, want_logits: bool = False):
+        """base.py:127-146 at per-layout timesteps: xt (B,S) ids, t (B,) -> log p(x0|xt) (B,S,C) [, logits (B,S,C)] on the GPU"""
+        B = xt.shape[0]
+        xt = xt.to(self.device, torch.int64).contiguous()
+        t32 = self._t32(t, B)
+        out = torch.empty(B, self.vocab.S, self.vocab.C, device=self.device)
+        lg = torch.empty_like(out) if want_logits else None
+        _lib.check(self.lib.ldm_predict_start(self._h, B, _ptr(xt), _ptr(t32), _ptr(out), _ptr(lg), self._stream()))
+        return (out, lg) if want_logits else out
+
+    def q_posterior(self, log_x_start: torch.Tensor, xt: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """constrained.py:135-206 / vanilla.py:112-151: log_x_start (B,S,C) any log p(x0), xt (B,S) ids, t (B,) -> (B,S,C)"""
+        B = xt.shape[0]
+        lx = log_x_start.to(self.device, torch.float32).contiguous()
+        assert lx.shape == (B, self.vocab.S, self.vocab.C)
+        xt = xt.to(self.device, torch.int64).contiguous()
+        t32 = self._t32(t, B)
+        out = torch.empty_like(lx)
+        _lib.check(self.lib.ldm_q_posterior(self._h, B, _ptr(lx), _ptr(xt), _ptr(t32), _ptr(out), self._stream()))
+        return out
+
+    def q_pred(self, log_x_start: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """constrained.py:112-133 on the full vocabulary: log_x_start (B,S,C), t (B,) in [-1, T) -> log q(x_t|x_0) (B,S,C)"""
+        B = log_x_start.shape[0]
+        lx = log_x_start.to(self.device, torch.float32).contiguous()
+        t32 = self._t32(t, B, lo=-1)
+        out = torch.empty_like(lx)
+        _lib.check(self.lib.ldm_q_pred(self._h, B, _ptr(lx), _ptr(t32), _ptr(out), self._stream()))
+        return out
+
+    def vb_terms(self, x0: torch.Tensor, xt: torch.Tensor, t: torch.Tensor, mask_weight=(1.0, 1.0), want_aux: bool = True,
+                 want_log_model_prob: bool = False, want_recon_ids: bool = False) -> Dict[str, torch.Tensor]:
+        """the per-layout loss terms of `forward` (constrained.py:262-333) after x_t has been drawn; tensors on the GPU"""
+        B = x0.shape[0]
+        x0 = x0.to(self.device, torch.int64).contiguous()
+        xt = xt.to(self.device, torch.int64).contiguous()
+        t32 = self._t32(t, B)
+        f = lambda: torch.empty(B, device=self.device)
+        kl, nll, aux = f(), f(), (f() if want_aux else None)
+        lmp = torch.empty(B, self.vocab.S, self.vocab.C, device=self.device) if want_log_model_prob else None
+        r0 = torch.empty_like(x0) if want_recon_ids else None
+        r1 = torch.empty_like(x0) if want_recon_ids else None
+        _lib.check(self.lib.ldm_vb_terms(self._h, B, _ptr(x0), _ptr(xt), _ptr(t32), C.c_float(mask_weight[0]), C.c_float(mask_weight[1]),
+                                         _ptr(kl), _ptr(nll), _ptr(aux), _ptr(lmp), _ptr(r0), _ptr(r1), self._stream()))
+        return {"kl": kl, "decoder_nll": nll, "kl_aux": aux, "log_model_prob": lmp, "x0_recon": r0, "xt_1_recon": r1}
+
     def decode(self, ids: torch.Tensor, centers: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """ids (B,S) on the GPU -> {"bbox" (B,E,4) f32, "label" (B,E) i64, "mask" (B,E) bool} on the GPU"""
         B = ids.shape[0]

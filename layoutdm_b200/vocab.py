@@ -51,6 +51,13 @@ class Vocab:
         return self.pad_id + 1
 
 
+def group_full_ids(vocab: "Vocab", g: int) -> List[int]:
+    """full-vocabulary ids of attribute g's partial vocabulary [its classes..., PAD, MASK] (Converter, layout_tokenizer.py:429-467)"""
+    lo = 0 if g == 0 else vocab.n_cat + (g - 1) * vocab.n_bins
+    n = vocab.n_cat if g == 0 else vocab.n_bins
+    return list(range(lo, lo + n)) + [vocab.pad_id, vocab.mask_id]
+
+
 def timestep_plan(T: int, T_eval: int, time_difference: float = 0.0) -> List[Tuple[int, int]]:
     """[(t_model, t_posterior)] per loop iteration."""
     assert T_eval <= T                                   # base.py:311

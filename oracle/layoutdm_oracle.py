@@ -227,8 +227,10 @@ def denoiser_forward(sd, ids: torch.Tensor, t: int, vocab: VocabSpec, spec: Mode
     h = sd[PREFIX + "cat_emb.weight"][ids] + positional_table(sd, vocab, spec)[None]   # nn_lib.py:204,220 (dropout = id in eval)
     for l in range(spec.layers):
         p = f"{PREFIX}backbone.layers.{l}."
-        emb = adaln_table(sd, spec, l)[t]                       # (2d,)
-        scale, shift = emb[:d], emb[d:]                         # torch.chunk(emb, 2)  transformer_utils.py:81
+        emb = adaln_table(sd, spec, l)[t]                       # (2d,); t may also be a (B,) tensor of per-layout timesteps (training)
+        if emb.dim() == 2:
+            emb = emb[:, None]                                  # .unsqueeze(1), transformer_utils.py:80
+        scale, shift = emb[..., :d], emb[..., d:]               # torch.chunk(emb, 2)  transformer_utils.py:81
         x = F.layer_norm(h, (d,), eps=1e-5) * (1 + scale) + shift   # :82
         tap(f"x{l}", x)
         # MHA(x,x,x): torch.nn.MultiheadAttention, batch_first, no masks (transformer_utils.py:140-142,197-204)
@@ -283,7 +285,7 @@ def _posterior_group(lp0: torch.Tensor, log_xt: torch.Tensor, is_mask: torch.Ten
     """One vocabulary group.  lp0, log_xt: (..., K) in the partial vocab [normal..., PAD, MASK];
     is_mask (..., 1) bool: x_t == MASK.  Literal transcription of constrained.py:163-197 with scalar t."""
     tm1 = (t - 1 + (T + 1)) % (T + 1)                           # :114
-    f = lambda name, i: tab[name][i]
+    f = (lambda name, i: tab[name][i].view(-1, 1, 1)) if torch.is_tensor(t) else (lambda name, i: tab[name][i])   # extract(), util.py:24-27
     # q(xt|x0): q_pred(log_x_t, t)   :112-133, :166-173
     log_qt = _log_add_exp(log_xt[..., :-1] + f("log_cumprod_at", t), f("log_cumprod_bt", t))
     log_qt = torch.where(is_mask, f("log_cumprod_ct", t).expand_as(log_qt), log_qt)
@@ -311,10 +313,10 @@ def index_to_log_onehot(ids: torch.Tensor, C: int) -> torch.Tensor:
 
 def q_posterior(log_x_recon: torch.Tensor, x_t: torch.Tensor, t: int, T: int, vocab: VocabSpec,
                 scheds: List[Dict[str, torch.Tensor]], q_type: str = "constrained") -> torch.Tensor:
-    """log_x_recon (B,S,C), x_t ids (B,S), scalar posterior timestep t -> log p(x_{t-1}|x_t) (B,S,C).
-    constrained: per attribute group gather -> maths -> scatter filled with log 1e-30
+    """log_x_recon (B,S,C), x_t ids (B,S), posterior timestep t (scalar, or a (B,) tensor of per-layout timesteps as in training)
+    -> log p(x_{t-1}|x_t) (B,S,C).  constrained: per attribute group gather -> maths -> scatter filled with log 1e-30
     (constrained.py:135-206; Converter.f_to_p_log / p_to_f_log, layout_tokenizer.py:540-557)."""
-    assert 0 <= t < T
+    assert (int(t.min()) >= 0 and int(t.max()) < T) if torch.is_tensor(t) else 0 <= t < T
     B, S, C = log_x_recon.shape
     log_xt = index_to_log_onehot(x_t, C)
     is_mask = (x_t == vocab.mask_id)[..., None]
@@ -329,6 +331,47 @@ def q_posterior(log_x_recon: torch.Tensor, x_t: torch.Tensor, t: int, T: int, vo
         tmp[..., idx] = pg
         out[:, sl] = tmp
     return out
+
+
+def q_pred_full(log_x_start: torch.Tensor, t: torch.Tensor, T: int, vocab: VocabSpec, scheds: List[Dict[str, torch.Tensor]],
+                q_type: str = "constrained") -> torch.Tensor:
+    """q_pred (constrained.py:112-133 per attribute on its partial vocabulary; vanilla.py:90-110) on full-vocabulary (B,S,C) log
+    tensors with per-layout timesteps t (B,) in [-1, T): classes outside a token's group stay log(1e-30) (p_to_f_log)."""
+    t = (t + (T + 1)) % (T + 1)
+    f = lambda tab, name: tab[name][t].view(-1, 1, 1)
+
+    def group(lx, tab):                                                 # lx (..., K) partial vocab [normal..., PAD, MASK]
+        return torch.cat([_log_add_exp(lx[..., :-1] + f(tab, "log_cumprod_at"), f(tab, "log_cumprod_bt")),
+                          _log_add_exp(lx[..., -1:] + f(tab, "log_1_min_cumprod_ct"), f(tab, "log_cumprod_ct"))], dim=-1)
+    if q_type == "vanilla":
+        return group(log_x_start, scheds[0])
+    out = torch.full_like(log_x_start, LOG_EPS)
+    S = log_x_start.shape[1]
+    for g in range(vocab.n_attr):
+        idx = torch.tensor(vocab.group_full_ids(g))
+        sl = slice(g, S, vocab.n_attr)
+        tmp = out[:, sl]
+        tmp[..., idx] = group(log_x_start[:, sl][..., idx], scheds[g])
+        out[:, sl] = tmp
+    return out
+
+
+def vb_terms(logits: torch.Tensor, x0: torch.Tensor, xt: torch.Tensor, t: torch.Tensor, T: int, vocab: VocabSpec,
+             scheds: List[Dict[str, torch.Tensor]], q_type: str = "constrained", mask_weight=(1.0, 1.0)) -> Dict[str, torch.Tensor]:
+    """The loss terms `forward` derives from the denoiser logits at x_t (constrained.py:262-325, vanilla.py:196-236), per layout:
+    kl (:295-302), decoder_nll (:304-305), kl_aux (:321-325), plus log_model_prob / log_x0_recon (B,S,C)."""
+    C = vocab.C
+    log_x0_recon = predict_start(logits)                                               # :263
+    log_model_prob = q_posterior(log_x0_recon, xt, t, T, vocab, scheds, q_type)        # :264-266
+    log_x_start = index_to_log_onehot(x0, C)
+    log_true_prob = q_posterior(log_x_start, xt, t, T, vocab, scheds, q_type)          # :295-297
+    kl = (log_true_prob.exp() * (log_true_prob - log_model_prob)).sum(-1)              # multinomial_kl, base.py:117-119
+    mask_region = (xt == C - 1).float()
+    w = mask_region * mask_weight[0] + (1.0 - mask_region) * mask_weight[1]
+    nll = -(log_x_start.exp() * log_model_prob).sum(-1)                                # log_categorical, util.py:30-31
+    aux = (log_x_start[..., :-1].exp() * (log_x_start[..., :-1] - log_x0_recon[..., :-1])).sum(-1)
+    return {"kl": (kl * w).mean(1), "decoder_nll": nll.mean(1), "kl_aux": (aux * w).mean(1),
+            "log_model_prob": log_model_prob, "log_x0_recon": log_x0_recon}
 
 
 # --------------------------------------------------------------------------------------------------------------

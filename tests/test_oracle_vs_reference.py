@@ -82,3 +82,71 @@ def test_make_cond_matches_reference_get_cond(ref, cond_type):
         assert torch.equal(want[k], got[k]), k
     if cond_type != "gt":
         assert torch.equal(want["num_element"], got["num_element"])
+
+
+@pytest.mark.parametrize("q_type", ["constrained", "vanilla"])
+def test_training_side_api_matches_reference(q_type):
+    """q_posterior with ANY log p(x0) and per-layout timesteps, q_pred, and the loss terms of `forward` (constrained.py:232-333 /
+    vanilla.py) -- oracle restatement vs the unmodified reference, with the reference's own x_t and (t, pt) injected"""
+    vocab, spec = O.RICO25, O.ModelSpec()
+    sd = O.make_weights(vocab, spec, seed=7, scale=2.0)
+    model, tok = rh.build_reference("rico25", T=100, q_type=q_type, state_dict=sd)
+    core = model.model.module
+    scheds = O.group_schedules(100, vocab, q_type)
+    B, S, C = 7, vocab.S, vocab.C
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.empty(B, S, dtype=torch.long)
+    for a in range(5):
+        ids = torch.tensor(vocab.group_full_ids(a)[:-1])
+        x0[:, a::5] = ids[torch.randint(0, len(ids), (B, 25), generator=g)]
+    t = torch.tensor([0, 1, 50, 99, 37, 0, 98])
+    xt = O.q_sample_ids(x0, t, 100, vocab, O.group_schedules(100, vocab), O.uniforms(3, 0, 2, 0, B, S, C))
+    log_xt = O.index_to_log_onehot(xt, C).permute(0, 2, 1)
+    # 1. q_posterior, arbitrary log p(x0)
+    lx = torch.log_softmax(torch.randn(B, S, C, generator=g) * 2.0, dim=-1).clamp(-70.0, 0.0)
+    with torch.no_grad():
+        want = core.q_posterior(log_x_start=lx.permute(0, 2, 1), log_x_t=log_xt, t=t).permute(0, 2, 1)
+    got = O.q_posterior(lx, xt, t, 100, vocab, scheds, q_type)
+    assert (got - want).abs().max() < 1e-5
+    # 2. q_pred (t = -1 wraps to T, constrained.py:115)
+    tq = torch.tensor([-1, 0, 50, 99, 37, 5, 98])
+    full = O.q_pred_full(lx, tq, 100, vocab, scheds, q_type)
+    if q_type == "constrained":
+        for a, key in enumerate("cxywh"):
+            idx = torch.tensor(vocab.group_full_ids(a))
+            part = lx[:, a::5][..., idx].permute(0, 2, 1)
+            with torch.no_grad():
+                w = core.q_pred(part, tq, key)
+            assert (full[:, a::5][..., idx].permute(0, 2, 1) - w).abs().max() < 1e-5
+    else:
+        with torch.no_grad():
+            w = core.q_pred(lx.permute(0, 2, 1), tq)
+        assert (full.permute(0, 2, 1) - w).abs().max() < 1e-5
+    # 3. forward: inject (t, pt) and the corruption so that the reference sees the same x_t
+    pt = torch.full((B,), 1.0 / 100)
+    core.sample_time = lambda b, device, method="uniform": (t, pt)
+    if q_type == "constrained":
+        def fake_q_sample(log_x_start, t, key):
+            a = "cxywh".index(key)
+            idx = torch.tensor(vocab.group_full_ids(a))
+            part = (xt[:, a::5][..., None] == idx).long().argmax(-1)
+            return torch.log(torch.nn.functional.one_hot(part, len(idx)).permute(0, 2, 1).float().clamp(min=1e-30))
+    else:
+        def fake_q_sample(log_x_start, t):
+            return log_xt
+    core.q_sample = fake_q_sample
+    with torch.no_grad():
+        outputs, losses = core.forward(x0, is_train=True)
+        logits = core.transformer(xt, timestep=t)["logits"]
+    r = O.vb_terms(logits, x0, xt, t, 100, vocab, scheds, q_type)
+    assert (r["log_model_prob"].exp().permute(0, 2, 1) - outputs["probs"]).abs().max() < 1e-5
+    mask = (t == 0).float()
+    kl_loss = mask * r["decoder_nll"] + (1 - mask) * r["kl"]
+    assert abs((kl_loss / pt).mean().item() - losses["kl_loss"].item()) < 1e-4 * abs(losses["kl_loss"].item())
+    aux = mask * r["decoder_nll"] + (1 - mask) * r["kl_aux"]
+    want_aux = (((1 - t / 100) + 1.0) * 0.1 * aux / pt).mean().item()
+    assert abs(want_aux - losses["aux_loss"].item()) < 1e-4 * abs(losses["aux_loss"].item())
+    # the oracle's denoiser at per-layout timesteps == the reference's transformer
+    with torch.no_grad():
+        lo = O.denoiser_forward(sd, xt, t, vocab, spec)
+    assert (lo - logits).abs().max() < 2e-5
