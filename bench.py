@@ -251,6 +251,44 @@ def gpu_eager_reference(B, dev):
             "what": f"unmodified reference LayoutDM.sample, fp32 PyTorch eager on the same GPU, batch {B} in chunks of <= 512, T={T}, one pass"}
 
 
+def other_configs(local):
+    """device-resident sample() at BASELINE.json configs 0 / 2 / 3 (synthetic weights and conditions); config 1 is the main line,
+    config 4 (8 x 1024) is what the N-GPU runs of this script measure"""
+    from layoutdm_b200 import Engine, Vocab, timestep_plan
+    from layoutdm_b200.synthetic import random_state_dict, synthetic_cond
+    cases = [("configs[0] rico25 unconditional, T_eval=50, batch=8", "rico25", 100, 50, 8, {"name": "random", "temperature": 1.0}, None, 5),
+             ("configs[2] publaynet cond=c, T=100, batch=1024, top_p=0.9", "publaynet", 100, 100, 1024, {"name": "top_p", "temperature": 1.0, "top_p": 0.9}, "c", 2),
+             ("configs[3] rico25 cond=refinement (logit masking), T=200, batch=4096", "rico25", 200, 200, 4096, {"name": "random", "temperature": 1.0}, "refinement", 2)]
+    out = []
+    for name, ds, Tm, T_eval, B, cfg, ctype, n in cases:
+        vocab = Vocab.for_dataset(ds)
+        eng = Engine.from_state_dict(random_state_dict(vocab, num_timesteps=Tm), vocab, num_timesteps=Tm, device=local)
+        cond = None
+        if ctype:
+            cond = {k: (v.cuda(local) if isinstance(v, torch.Tensor) else v) for k, v in synthetic_cond(vocab, B, ctype).items()}
+        plan = timestep_plan(Tm, T_eval)
+        ids0 = cond["seq"] if cond else None
+        for w in range(3 if B < 1024 else 1):
+            eng.sample_loop(B, plan, cfg, cond=cond, seed=1 + w, ids_init=ids0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            ids = eng.sample_loop(B, plan, cfg, cond=cond, seed=10 + i, ids_init=ids0)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        if cond is not None:
+            assert torch.equal(ids[cond["mask"]], cond["seq"][cond["mask"]])      # strong conditioning reproduced exactly
+        assert int(ids.max()) < vocab.C - 1                                       # no MASK left
+        out.append({"config": name, "ms_per_step": round(ms, 3), "layouts_per_s": round(B / (ms * 1e-3), 1),
+                    "ms_per_denoising_iteration": round(ms / T_eval, 4), "passes_timed": n})
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+    return out
+
+
 # --------------------------------------------------------------------------------------------------------------
 def run_b200_arm(args, world, rank, local):
     from layoutdm_b200 import Engine, Vocab, timestep_plan
@@ -262,6 +300,10 @@ def run_b200_arm(args, world, rank, local):
     vocab = Vocab.for_dataset("rico25")
     eng = Engine.from_state_dict(random_state_dict(vocab, num_timesteps=T, seed=0), vocab, num_timesteps=T, operand_dtype=args.dtype, device=local)
     B = args.batch                                    # per GPU (weak scaling: configs[4] = 8 x 1024)
+    strong = args.total_batch > 0
+    if strong:
+        assert args.total_batch % world == 0
+        B = args.total_batch // world
     total = B * world
     plan = timestep_plan(T, T)
     cfg = {"name": "random", "temperature": 1.0}
@@ -328,6 +370,11 @@ def run_b200_arm(args, world, rank, local):
                 "path_tflops": value / world * T * FLOPS_PER_LAYOUT_STEP / 1e12,
                 "path_frac": value / world * T * FLOPS_PER_LAYOUT_STEP / 1e12 / peaks["sustained"]}
 
+    # ---- the other single-GPU BASELINE.json configs (rank 0, N=1 only): parity-test cases, reported as sub-records ----
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        configs = other_configs(local)
+
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores; reference on the same GPU ----
     cpu = gpu_eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -344,13 +391,13 @@ def run_b200_arm(args, world, rank, local):
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": "rico25 unconditional, T=100, batch=1024 per GPU, N=25 (S=125 tokens, C=155), sampling=random, random-init weights",
+                "config": {"workload": f"rico25 unconditional, T=100, batch={B} per GPU, N=25 (S=125 tokens, C=155), sampling=random, random-init weights",
                            "global_batch": total, "parallelism": f"dp{world} (batch-sharded replicas, one all-gather of ids)" if world > 1 else "single GPU",
                            "l2": "per-step activation working set (1.9 GB at B=1024) >> 126 MB L2, no explicit flush needed",
                            "operands": f"{args.dtype} tensor-core operands, fp32 accumulate / LayerNorm / softmax / posterior"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "configs": configs}
         print(json.dumps(line), flush=True)
 
 
@@ -363,6 +410,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the sub-records of BASELINE.json configs 0 / 2 / 3")
+    ap.add_argument("--total-batch", type=int, default=0, help="strong scaling: this many layouts in total, split over the ranks")
     args = ap.parse_args()
     if args.impl == "reference":
         world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))

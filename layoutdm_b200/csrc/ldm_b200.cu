@@ -545,6 +545,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   h->desc = *desc; h->C = C; h->S = S; h->L = L; h->T = T; h->bf16 = desc->operand_dtype == 1;
   h->G = desc->q_type == 0 ? desc->n_attr : 1;
   h->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("LDM_NUM_SMS")) { const int v = atoi(e); if (v >= 4 && v <= h->num_sms) h->num_sms = v; }   // experiments: persistent grids sized for a share of the GPU
   if (const char* e = getenv("LDM_GEMM_DEBUG")) h->gemm_dbg = atoi(e);
   if (const char* e = getenv("LDM_GENERIC_POSTERIOR")) h->debug_generic_posterior = atoi(e);
   if (const char* e = getenv("LDM_PDL")) h->pdl = atoi(e);
