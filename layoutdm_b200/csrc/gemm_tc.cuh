@@ -62,7 +62,9 @@ struct GemmParams {
   const int* t_layout;    // EPI_LN + adaln: per-layout timesteps (training-side calls): ln_scale then points at the layer's whole [T][2N]
   int n_layouts;          //   AdaLN table and every (row block, CTA) = layout reloads its (scale, shift) row; nullptr: one timestep for all
   int tile_sched;         // 1: spread single (row block, N tile) tiles over the CTA pairs (small batches); 0: a pair walks all N tiles of a row block
-  int dbg;                // bring-up probe (env LDM_GEMM_DEBUG), bit mask: 1 = skip the MMAs, 2 = skip the TMA operand loads, 4 = skip the epilogue body; results are garbage
+  int dbg;                // bring-up probe (env LDM_GEMM_DEBUG), bit mask: 1 = skip the MMAs, 2 = skip the TMA operand loads, 4 = skip the epilogue body,
+                          // 8 = every epilogue store is issued out of bounds (the TMA engine reads the staging tile but writes nothing),
+                          // 16 = every epilogue store lands in the first 256 rows (an L2-resident window: no HBM write stream); results are garbage
 };
 
 constexpr int kAResSlots = 8;   // A-resident mode: K <= 512, the row block's whole A operand (8 k-blocks) stays in smem
@@ -284,7 +286,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tlane = static_cast<uint32_t>(quad * 32) << 16;
 
     // stage one 32 x 32 block (this warp's rows, 32 columns) and hand it to the TMA engine
+    const int st_or = (p.dbg & 8) ? 0x40000000 : 0, st_and = (p.dbg & 16) ? 255 : 0x7fffffff;   // store-stream probes (see GemmParams::dbg)
     auto store_f32 = [&](const CUtensorMap* m, const float* v, int col, int row0) {
+      row0 = (row0 & st_and) | st_or;
       if (lane == 0) bulk_wait_read0();        // earlier stores have finished reading the staging buffers
       __syncwarp();
 #pragma unroll
@@ -296,6 +300,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (lane == 0) { tma_store_2d(m, s32, col, row0); bulk_commit(); }
     };
     auto store_16 = [&](const CUtensorMap* m, const float* v, int col, int row0) {
+      row0 = (row0 & st_and) | st_or;
       if (lane == 0) bulk_wait_read0();
       __syncwarp();
 #pragma unroll
