@@ -92,6 +92,13 @@ LDM_DEVINL void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int32_t 
 }
 LDM_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 LDM_DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // staged sources reusable
+// all but the `pending` most recent bulk groups of this thread have finished reading their shared-memory source
+LDM_DEVINL void bulk_wait_read_pending(int pending) {
+  if (pending <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  else if (pending == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  else if (pending == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+}
 LDM_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }          // stores complete
 
 // multicast variant: the tile lands at the same smem offset (and signals the same-offset mbarrier) in every CTA of `mask`

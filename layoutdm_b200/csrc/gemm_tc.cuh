@@ -67,6 +67,9 @@ struct GemmParams {
                           // 16 = every epilogue store lands in the first 256 rows (an L2-resident window: no HBM write stream); results are garbage
 };
 
+#ifndef LDM_ARES_STORE_BUFS
+#define LDM_ARES_STORE_BUFS 1      // 2: two alternating store blocks per epilogue warp at the price of one weight stage -- measured SLOWER
+#endif                             // (QKV 158 -> 176 us, FF1 196 -> 221 us): the stores do not wait on their staging block, they slow the operand loads
 constexpr int kAResSlots = 8;   // A-resident mode: K <= 512, the row block's whole A operand (8 k-blocks) stays in smem
 
 // ARES: the 128 x K activation block of the CTA is loaded ONCE per row block and reused by all N tiles; only the weight
@@ -85,7 +88,9 @@ struct GemmSmem {
   static constexpr bool kLnExtraBuf = EPI == EPI_LN && STAGES <= 3;
   // LN with a long ring (FF2, K = 1856): compact staging, the 16-bit store block [4K,6K) shares the residual block [4K,8K)
   static constexpr bool kLnCompact = EPI == EPI_LN && STAGES >= 5;
-  static constexpr int kWarpStage = EPI == EPI_LN ? (kLnExtraBuf ? 14336 : (kLnCompact ? 8192 : 10240)) : (ARES ? 2048 : 4096);
+  // plain 16-bit epilogues (ARES: QKV / FF1): kStoreBufs alternating 2 KB store blocks per warp (experiment, see LDM_ARES_STORE_BUFS)
+  static constexpr int kStoreBufs = (EPI != EPI_LN && ARES) ? LDM_ARES_STORE_BUFS : 1;
+  static constexpr int kWarpStage = EPI == EPI_LN ? (kLnExtraBuf ? 14336 : (kLnCompact ? 8192 : 10240)) : (ARES ? 2048 * kStoreBufs : 4096);
   static constexpr int kStagingBytes = 8 * kWarpStage;
   static constexpr int kBarBytes = 512;
   // bias vector of the layer; LN: bias / gamma / beta of the CTA's own column tile (a pair keeps its tile), 256 floats each
@@ -286,10 +291,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tlane = static_cast<uint32_t>(quad * 32) << 16;
 
     // stage one 32 x 32 block (this warp's rows, 32 columns) and hand it to the TMA engine
-    const int st_or = (p.dbg & 8) ? 0x40000000 : 0, st_and = (p.dbg & 16) ? 255 : 0x7fffffff;   // store-stream probes (see GemmParams::dbg)
+    const int st_or = (p.dbg & 8) ? 0x40000000 : 0, st_and = (p.dbg & 16) ? 8191 : 0x7fffffff;   // store-stream probes (see GemmParams::dbg)
+    // Staging blocks are recycled per block, not per warp: every TMA store is its own bulk group, groups retire in order, so before a
+    // block is rewritten only the groups up to its previous store have to have left shared memory -- the newer ones stay in flight.
+    int n_groups = 0, last_g16[2] = {-1000, -1000}, last_g32 = -1000;
+    uint32_t buf16 = 0;                        // which of the kStoreBufs 16-bit blocks the next store uses
+    // stage one 32 x 32 block (this warp's rows, 32 columns) and hand it to the TMA engine
     auto store_f32 = [&](const CUtensorMap* m, const float* v, int col, int row0) {
       row0 = (row0 & st_and) | st_or;
-      if (lane == 0) bulk_wait_read0();        // earlier stores have finished reading the staging buffers
+      if (lane == 0) bulk_wait_read_pending(n_groups - 1 - last_g32);
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -298,19 +308,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) { tma_store_2d(m, s32, col, row0); bulk_commit(); }
+      last_g32 = n_groups++;
     };
     auto store_16 = [&](const CUtensorMap* m, const float* v, int col, int row0) {
       row0 = (row0 & st_and) | st_or;
-      if (lane == 0) bulk_wait_read0();
+      const uint32_t sb = s16 + (SM::kStoreBufs > 1 ? buf16 * 2048u : 0u);
+      if (lane == 0) bulk_wait_read_pending(n_groups - 1 - last_g16[buf16]);
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        sts_u4(s16 + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4),
+        sts_u4(sb + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4),
                make_uint4(O::pack(v[8 * c], v[8 * c + 1]), O::pack(v[8 * c + 2], v[8 * c + 3]),
                           O::pack(v[8 * c + 4], v[8 * c + 5]), O::pack(v[8 * c + 6], v[8 * c + 7])));
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { tma_store_2d(m, s16, col, row0); bulk_commit(); }
+      if (lane == 0) { tma_store_2d(m, sb, col, row0); bulk_commit(); }
+      last_g16[buf16] = n_groups++;
+      if (SM::kStoreBufs > 1) buf16 ^= 1u;
     };
 
     int acc = 0; uint32_t acc_phase = 0;

@@ -41,6 +41,8 @@ constexpr int kQkvN = 3 * 8 * kHeadPad;   // 1536
 constexpr int kAttN = 8 * kHeadPad;        // 512: attention output, heads padded like Q/K/V
 constexpr int kLogitLd = 160;       // padded logits row (C <= 160)
 constexpr int kDModel = 464;        // the kernels are laid out for the paper's backbone: d = 464 (LN tiles 224 + 240), ff = 4 d
+// A-resident GEMMs (QKV, FF1): weight-ring depth.  Two alternating store blocks per epilogue warp cost the shared memory of one stage.
+constexpr int kAresStages = LDM_ARES_STORE_BUFS >= 2 ? 4 : 5;
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -364,7 +366,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       GemmParams p{M, kQkvN, d, kQkvN / 256, h->bqkv[l], h->qkv16, kQkvN, 1.0f / sqrtf(static_cast<float>(d / h->desc.n_heads)), 8 * kHeadPad};
       p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles);
       ProfScope ps(h, CAT_QKV, st);
-      CK(launch_step(h, gemm_tc_kernel<256, 256, 5, EPI_QKV, BF16, true>, pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 5, EPI_QKV, true>::kBytes, st, false,
+      CK(launch_step(h, gemm_tc_kernel<256, 256, kAresStages, EPI_QKV, BF16, true>, pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, kAresStages, EPI_QKV, true>::kBytes, st, false,
                      h->m_x16, h->m_wqkv[l], h->b_qkv16, h->b_qkv16, h->b_qkv16, h->t_x16, p));
     }
     LDM_STAGE_DONE();
@@ -386,7 +388,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       GemmParams p{M, ff, d, (ff + 255) / 256, h->b1[l], h->hid16, ff, 1.0f, 0};   // 7 tiles of 256 columns + one of 64
       p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles);
       ProfScope ps(h, CAT_FF1, st);
-      CK(launch_step(h, gemm_tc_kernel<256, 256, 5, EPI_RELU, BF16, true>, pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, 5, EPI_RELU, true>::kBytes, st, false,
+      CK(launch_step(h, gemm_tc_kernel<256, 256, kAresStages, EPI_RELU, BF16, true>, pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, kAresStages, EPI_RELU, true>::kBytes, st, false,
                      h->m_z16, h->m_w1[l], h->b_hid16, h->b_hid16, h->b_hid16, h->t_z16, p));
     }
     LDM_STAGE_DONE();
@@ -633,15 +635,15 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   free_staging(h);
 
   if (h->bf16) {
-    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, true, true>, GemmSmem<256, 5, EPI_QKV, true>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_RELU, true, true>, GemmSmem<256, 5, EPI_RELU, true>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, kAresStages, EPI_QKV, true, true>, GemmSmem<256, kAresStages, EPI_QKV, true>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, kAresStages, EPI_RELU, true, true>, GemmSmem<256, kAresStages, EPI_RELU, true>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, true>, GemmSmem<160, 5, EPI_F32>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<224, 240, 5, EPI_LN, true>, GemmSmem<240, 5, EPI_LN>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<224, 240, 3, EPI_LN, true>, GemmSmem<240, 3, EPI_LN>::kBytes)));
     TRY((set_smem(attention_kernel<true>, kAttSmemBytes)));
   } else {
-    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_QKV, false, true>, GemmSmem<256, 5, EPI_QKV, true>::kBytes)));
-    TRY((set_smem(gemm_tc_kernel<256, 256, 5, EPI_RELU, false, true>, GemmSmem<256, 5, EPI_RELU, true>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, kAresStages, EPI_QKV, false, true>, GemmSmem<256, kAresStages, EPI_QKV, true>::kBytes)));
+    TRY((set_smem(gemm_tc_kernel<256, 256, kAresStages, EPI_RELU, false, true>, GemmSmem<256, kAresStages, EPI_RELU, true>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<160, 160, 5, EPI_F32, false>, GemmSmem<160, 5, EPI_F32>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<224, 240, 5, EPI_LN, false>, GemmSmem<240, 5, EPI_LN>::kBytes)));
     TRY((set_smem(gemm_tc_kernel<224, 240, 3, EPI_LN, false>, GemmSmem<240, 3, EPI_LN>::kBytes)));
