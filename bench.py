@@ -29,6 +29,16 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
+# stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library chatter from C code)
+# is sent to stderr; the line itself goes to the saved descriptor
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: str):
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
 METRIC = "layouts_per_sec_T100_batch1024_N25"
 UNIT = "layouts/s"
 T = 100
@@ -222,7 +232,7 @@ def run_reference_arm(args, world, rank):
             "cpu_baseline": {"value": lps, "unit": UNIT, "cores": cores, "kind": arm.kind, "sample": arm.sample_desc(dt),
                              "best_step_value": arm.layouts_per_s(min(dts)), "step_seconds": [round(x, 3) for x in dts]},
             "e2e": {"value": lps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def gpu_eager_reference(B, dev):
@@ -398,7 +408,7 @@ def run_b200_arm(args, world, rank, local):
                            "l2": "per-step activation working set (1.9 GB at B=1024) >> 126 MB L2, no explicit flush needed",
                            "operands": f"{args.dtype} tensor-core operands, fp32 accumulate / LayerNorm / softmax / posterior"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "configs": configs}
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
 
 
 def main():
