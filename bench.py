@@ -46,6 +46,11 @@ T = 100
 FLOPS = {"qkv_gemm": 161_472_000, "outproj_gemm": 53_824_000, "ff1_gemm": 215_296_000, "ff2_gemm": 215_296_000,
          "attention": 29_000_000, "head_gemm": 17_980_000}
 FLOPS_PER_LAYOUT_STEP = 2_717_532_000
+# algorithmic HBM bytes per layout per launch (rows of 128 tokens; x16/z16 119 KB, x32/y32 237 KB, qkv16 393 KB, att16 131 KB,
+# hid16 475 KB, logits 82 KB): what each kernel must read + write when every intermediate makes one round trip through HBM
+BYTES = {"embed_adaln": 237_568 + 118_784, "qkv_gemm": 118_784 + 393_216, "attention": 393_216 + 131_072,
+         "outproj_gemm": 131_072 + 2 * 237_568 + 118_784, "ff1_gemm": 118_784 + 475_136, "ff2_gemm": 475_136 + 2 * 237_568 + 118_784,
+         "head_gemm": 118_784 + 81_920, "posterior_sample": 81_920 + 2_000}
 
 
 def load_traffic(kernel):
@@ -375,8 +380,11 @@ def run_b200_arm(args, world, rank, local):
                 "algorithmic_flops_per_launch": FLOPS[dom] * B, "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
                 "share_of_step": dom_ms / tot_prof,
                 "kernels": {k: {"ms_per_pass": round(v[0], 3), "launches": v[1], "share": round(v[0] / tot_prof, 4),
-                                **({"tflops": round(FLOPS[k] * B / (v[0] / v[1] * 1e-3) / 1e12, 1)} if k in FLOPS and v[1] else {})}
+                                **({"tflops": round(FLOPS[k] * B / (v[0] / v[1] * 1e-3) / 1e12, 1)} if k in FLOPS and v[1] else {}),
+                                **({"hbm_gbs": round(BYTES[k] * B / (v[0] / v[1] * 1e-3) / 1e9, 0),
+                                    "hbm_frac": round(BYTES[k] * B / (v[0] / v[1] * 1e-3) / 1e9 / peaks["hbm"], 3)} if k in BYTES and v[1] else {})}
                             for k, v in prof.items() if v[1]},
+                "hbm_peak_gbs": peaks["hbm"],
                 "path_tflops": value / world * T * FLOPS_PER_LAYOUT_STEP / 1e12,
                 "path_frac": value / world * T * FLOPS_PER_LAYOUT_STEP / 1e12 / peaks["sustained"]}
 

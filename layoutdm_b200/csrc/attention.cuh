@@ -114,7 +114,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
         }
         __syncwarp();
       }
-      bulk_wait_all();
+      bulk_wait_read0();                                       // the staging tiles have been read; the writes complete with the grid
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================

@@ -42,28 +42,15 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, void* __restri
   }
 }
 
+// one token row: h = cat_emb[id] + pos[s]; x = LN(h) * (1 + scale_t) + shift_t -> fp32 residual row + 16-bit operand row (whole warp)
 template <bool BF16>
-__global__ void __launch_bounds__(256)
-embed_adaln_kernel(const long long* __restrict__ ids /*[B][S]*/, const float* __restrict__ cat_emb /*[C][d]*/,
-                   const float* __restrict__ pos /*[S][d]*/, const float* __restrict__ adaln_tab /*[T][2d] of layer 0*/, int t_model,
-                   const int* __restrict__ t_layout /*[n_layouts] per-layout timesteps (training-side calls) or nullptr*/,
-                   float* __restrict__ x32 /*[B*128][d]*/, void* __restrict__ x16_, int n_layouts, int n_layouts_padded, int S, int d) {
+LDM_DEVINL void embed_token_row(const long long id, const int s, const size_t row, const float* __restrict__ cat_emb, const float* __restrict__ pos,
+                                const float* __restrict__ adaln /*[2d] of (layer 0, t)*/, float* __restrict__ x32, void* __restrict__ x16_, const int d, const int lane) {
   using O = OpT<BF16>;
   typename O::T* x16 = static_cast<typename O::T*>(x16_);
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp_global >= n_layouts_padded * 128) return;
-  pdl_sync();                                // ids come from the previous step's draw; x32 / x16 may still be read by it
-  const int b = warp_global >> 7, s = warp_global & 127;
-  const size_t row = static_cast<size_t>(warp_global);
   const int nv = d / 4;                      // float4 per row (464 / 4 = 116)
   float4* o32 = reinterpret_cast<float4*>(x32 + row * d);
   uint2* o16 = reinterpret_cast<uint2*>(x16 + row * d);
-  if (s >= S || b >= n_layouts) {      // padding rows / padding layout of an odd batch
-    for (int i = lane; i < nv; i += 32) { o32[i] = make_float4(0.f, 0.f, 0.f, 0.f); o16[i] = make_uint2(0u, 0u); }
-    return;
-  }
-  const long long id = ids[static_cast<size_t>(b) * S + s];
-  const float* adaln = adaln_tab + static_cast<size_t>(t_layout != nullptr ? __ldg(t_layout + b) : t_model) * 2 * d;
   const float4* e = reinterpret_cast<const float4*>(cat_emb + static_cast<size_t>(id) * d);
   const float4* p = reinterpret_cast<const float4*>(pos + static_cast<size_t>(s) * d);
   float4 v[4];
@@ -105,6 +92,31 @@ embed_adaln_kernel(const long long* __restrict__ ids /*[B][S]*/, const float* __
       o16[i] = make_uint2(O::pack(r.x, r.y), O::pack(r.z, r.w));
     }
   }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+embed_adaln_kernel(const long long* __restrict__ ids /*[B][S]*/, const float* __restrict__ cat_emb /*[C][d]*/,
+                   const float* __restrict__ pos /*[S][d]*/, const float* __restrict__ adaln_tab /*[T][2d] of layer 0*/, int t_model,
+                   const int* __restrict__ t_layout /*[n_layouts] per-layout timesteps (training-side calls) or nullptr*/,
+                   float* __restrict__ x32 /*[B*128][d]*/, void* __restrict__ x16_, int n_layouts, int n_layouts_padded, int S, int d) {
+  using O = OpT<BF16>;
+  typename O::T* x16 = static_cast<typename O::T*>(x16_);
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp_global >= n_layouts_padded * 128) return;
+  pdl_sync();                                // ids come from the previous step's draw; x32 / x16 may still be read by it
+  const int b = warp_global >> 7, s = warp_global & 127;
+  const size_t row = static_cast<size_t>(warp_global);
+  if (s >= S || b >= n_layouts) {      // padding rows / padding layout of an odd batch
+    const int nv = d / 4;
+    float4* o32 = reinterpret_cast<float4*>(x32 + row * d);
+    uint2* o16 = reinterpret_cast<uint2*>(x16 + row * d);
+    for (int i = lane; i < nv; i += 32) { o32[i] = make_float4(0.f, 0.f, 0.f, 0.f); o16[i] = make_uint2(0u, 0u); }
+    return;
+  }
+  const long long id = ids[static_cast<size_t>(b) * S + s];
+  const float* adaln = adaln_tab + static_cast<size_t>(t_layout != nullptr ? __ldg(t_layout + b) : t_model) * 2 * d;
+  embed_token_row<BF16>(id, s, row, cat_emb, pos, adaln, x32, x16_, d, lane);
 }
 
 }  // namespace ldm

@@ -520,7 +520,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-    if (lane == 0) bulk_wait_all();            // this warp's TMA stores have completed before the CTA retires
+    if (lane == 0) bulk_wait_read0();          // this warp's TMA stores have read their staging blocks before the CTA retires (the writes
+                                               // themselves complete with the grid: a dependent kernel's griddepcontrol.wait covers them)
   }
 
   tc_fence_before();

@@ -160,6 +160,7 @@ struct LdmHandle {
   // CUDA graph of the whole T-step loop (ldm_sample_loop): captured once per (batch, plan, sampling, conditioning kind) and
   // replayed; everything that changes from call to call lives in device memory (noise key block, staged cond / start ids)
   int use_graph = 1;           // env LDM_GRAPH=0: plain stream launches
+  int fuse_embed = 1;          // env LDM_FUSE_EMBED=0: the loop launches the embedding kernel in every step instead of fusing it into the previous draw
   cudaStream_t cap_stream = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   uint64_t graph_key = 0;
@@ -340,7 +341,7 @@ int ensure_workspace(LdmHandle* h, int n_layouts) {
 }
 
 template <bool BF16>
-int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, cudaStream_t st, const int* t_layout = nullptr) {
+int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, cudaStream_t st, const int* t_layout = nullptr, bool skip_embed = false) {
   const int d = h->desc.d_model, ff = h->desc.d_ff, L = h->L, T = h->T;
   const int np = (n + 1) & ~1;            // layouts incl. the padding layout of an odd batch
   const int M = np * kBM;
@@ -354,13 +355,13 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
   int done = 0;
   // test tap: stop after `debug_stop_after` launches
 #define LDM_STAGE_DONE() do { if (h->debug_stop_after && ++done >= h->debug_stop_after) { CK(cudaGetLastError()); return LDM_OK; } } while (0)
-  {
+  if (!skip_embed) {     // skipped inside the loop: the previous step's draw kernel has already written this step's x32 / x16 rows
     const int warps = np * 128, blocks = (warps * 32 + 255) / 256;
     ProfScope ps(h, CAT_EMBED, st);
     CK(launch_step(h, embed_adaln_kernel<BF16>, blocks, 256, 0, st, false, ids_in, (const float*)h->cat_emb, (const float*)h->pos,
                    (const float*)h->adaln, t_model, t_layout, h->x32, h->x16, n, np, h->S, d));
   }
-  LDM_STAGE_DONE();
+  if (!skip_embed) LDM_STAGE_DONE();
   for (int l = 0; l < L; ++l) {
     {  // QKV projection (+bias, q * 1/sqrt(head_dim))
       GemmParams p{M, kQkvN, d, kQkvN / 256, h->bqkv[l], h->qkv16, kQkvN, 1.0f / sqrtf(static_cast<float>(d / h->desc.n_heads)), 8 * kHeadPad};
@@ -433,7 +434,8 @@ int validate_common(LdmHandle* h, int B, const LdmSampling* s) {
 
 int step_impl(LdmHandle* h, int B, const long long* ids_in, int t_model, int t_post, const LdmCond* cond, const LdmSampling* samp,
               uint64_t seed, uint32_t step_ctr, int64_t b_global0, long long* ids_out, float* logits_out, float* logprob_out,
-              const float* logits_in, const float* logprob_in, cudaStream_t st, const unsigned long long* call = nullptr) {
+              const float* logits_in, const float* logprob_in, cudaStream_t st, const unsigned long long* call = nullptr,
+              bool skip_embed = false, int t_next = -1) {
   if (t_model < 0 || t_model >= h->T || t_post < 0 || t_post >= h->T)
     return fail(LDM_ERR_INVALID, "timestep out of range: t_model=%d t_post=%d T=%d (constrained.py:139)", t_model, t_post, h->T);
   int rc = ensure_workspace(h, B);
@@ -443,7 +445,7 @@ int step_impl(LdmHandle* h, int B, const long long* ids_in, int t_model, int t_p
       ProfScope ps(h, CAT_MISC, st);
       logits_scatter_kernel<<<1024, 256, 0, st>>>(logits_in, h->logits, B, h->S, h->C);
     } else {
-      rc = h->bf16 ? launch_denoiser<true>(h, B, ids_in, t_model, st) : launch_denoiser<false>(h, B, ids_in, t_model, st);
+      rc = h->bf16 ? launch_denoiser<true>(h, B, ids_in, t_model, st, nullptr, skip_embed) : launch_denoiser<false>(h, B, ids_in, t_model, st, nullptr, skip_embed);
       if (rc) return rc;
     }
     if (logits_out != nullptr) {
@@ -470,6 +472,10 @@ int step_impl(LdmHandle* h, int B, const long long* ids_in, int t_model, int t_p
   p.mode = samp->mode; p.temperature = samp->temperature; p.top_p = samp->top_p; p.top_k = samp->top_k;
   p.seed = seed; p.step_ctr = step_ctr; p.b_global0 = b_global0; p.call = call;
   p.ids_out = ids_out; p.logprob_out = logprob_out;
+  if (t_next >= 0) {     // the loop: this draw also writes the next step's embedding + AdaLN_0(t_next) rows
+    p.emb_cat = h->cat_emb; p.emb_pos = h->pos; p.emb_adaln = h->adaln + static_cast<size_t>(t_next) * 2 * h->desc.d_model;
+    p.emb_x32 = h->x32; p.emb_x16 = h->x16; p.emb_d = h->desc.d_model; p.emb_bf16 = h->bf16 ? 1 : 0;
+  }
   const int warps = B * h->S, blocks = (warps * 32 + 255) / 256;
   // cond = relation on the device (base.py:243-284 order: strong mask [+ refinement prior] -> update() -> PAD-disable -> draw):
   //   1. posterior kernel -> log-probs with PAD-disable OFF into rel_lp   2. relation_update_kernel in place
@@ -480,7 +486,7 @@ int step_impl(LdmHandle* h, int B, const long long* ids_in, int t_model, int t_p
       return fail(LDM_ERR_UNSUPPORTED, "relation update needs the c-x-y-w-h layout with <= 31 elements and <= 32 bins");
     if (!h->rel_lp) CK(cudaMalloc(reinterpret_cast<void**>(&h->rel_lp), static_cast<size_t>(h->cap) * h->S * h->C * sizeof(float)));
     StepParams p1 = p;
-    p1.cond_flags &= ~COND_PAD_DISABLE; p1.logprob_out = h->rel_lp;
+    p1.cond_flags &= ~COND_PAD_DISABLE; p1.logprob_out = h->rel_lp; p1.emb_adaln = nullptr;    // its draw is discarded: no embedding
     {
       ProfScope ps(h, CAT_EPILOGUE, st);
       CK(launch_step(h, posterior_sample_kernel, blocks, 256, 0, st, false, p1));
@@ -552,6 +558,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   if (const char* e = getenv("LDM_GENERIC_POSTERIOR")) h->debug_generic_posterior = atoi(e);
   if (const char* e = getenv("LDM_PDL")) h->pdl = atoi(e);
   if (const char* e = getenv("LDM_GRAPH")) h->use_graph = atoi(e);
+  if (const char* e = getenv("LDM_FUSE_EMBED")) h->fuse_embed = atoi(e);
 #define TRY(x) do { rc = (x); if (rc) { ldm_destroy(h); return rc; } } while (0)
 
   TRY(dev_upload(h, &h->cat_emb, w->cat_emb, static_cast<size_t>(C) * d));
@@ -712,7 +719,9 @@ int run_loop(LdmHandle* h, int B, int n_steps, const int32_t* t_model, const int
     if (ids_trace) dst = ids_trace + static_cast<size_t>(i) * nid;
     else if (i == n_steps - 1) dst = ids_out;
     else dst = (cur == h->ids[0]) ? h->ids[1] : h->ids[0];
-    int rc = step_impl(h, B, cur, t_model[i], t_post[i], cond, sampling, seed, static_cast<uint32_t>(i), b_global0, dst, nullptr, nullptr, nullptr, nullptr, st, call);
+    const bool fuse = h->fuse_embed != 0;
+    int rc = step_impl(h, B, cur, t_model[i], t_post[i], cond, sampling, seed, static_cast<uint32_t>(i), b_global0, dst, nullptr, nullptr, nullptr, nullptr, st, call,
+                       fuse && i > 0, (fuse && i + 1 < n_steps) ? t_model[i + 1] : -1);
     if (rc) return rc;
     cur = dst;
   }
@@ -773,7 +782,7 @@ int ldm_sample_loop(LdmHandle* h, int32_t B, int32_t n_steps, const int32_t* t_m
   CK(cudaMemcpyAsync(h->call_block, blk, sizeof(blk), cudaMemcpyHostToDevice, st));   // pageable source: staged by the driver before the call returns
 
   uint64_t key = 1469598103934665603ull;
-  const int32_t head[6] = {B, n_steps, has_cond ? 1 + (gc.mask ? 2 : 0) + (gc.seq_orig ? 4 : 0) + (gc.pad_disable ? 8 : 0) : 0, ids_init ? 1 : 0, h->pdl, 0};
+  const int32_t head[6] = {B, n_steps, has_cond ? 1 + (gc.mask ? 2 : 0) + (gc.seq_orig ? 4 : 0) + (gc.pad_disable ? 8 : 0) : 0, ids_init ? 1 : 0, h->pdl, h->fuse_embed};
   key = fnv1a(key, head, sizeof(head));
   key = fnv1a(key, t_model, sizeof(int32_t) * n_steps);
   key = fnv1a(key, t_post, sizeof(int32_t) * n_steps);

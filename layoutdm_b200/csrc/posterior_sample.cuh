@@ -9,6 +9,7 @@
 // Class ownership inside a warp: lane l holds classes 4l..4l+3 (one float4 of logits, one Philox block) and class 128+l.
 #pragma once
 #include "common.cuh"
+#include "embed.cuh"
 
 namespace ldm {
 
@@ -38,6 +39,10 @@ struct StepParams {
                                          // CUDA graph of the loop stays valid while the noise key changes from call to call
   long long* ids_out;                    // [n_layouts][S]
   float* logprob_out;                    // [n_layouts][S][C] or nullptr
+  // the front of the NEXT denoising step, fused behind the draw (the loop API only): the warp that drew a token also writes that
+  // token's embedding + AdaLN_0(t_next) row, which saves the embed launch and overlaps its write stream with this issue-bound kernel
+  const float* emb_cat; const float* emb_pos; const float* emb_adaln;   // cat_emb [C][d], pos [S][d], AdaLN row [2d] of (layer 0, t_next); emb_adaln == nullptr: off
+  float* emb_x32; void* emb_x16; int emb_d, emb_bf16;
 };
 
 LDM_DEVINL float log_add_exp(float a, float b) {   // util.py:19-21
@@ -59,6 +64,14 @@ __global__ void lae_table_kernel(const float* __restrict__ sched, float* __restr
   o.x = log_add_exp(0.0f + lcat, lcbt); o.y = log_add_exp(kLogEps + lcat, lcbt);
   o.z = log_add_exp(0.0f + lat, lbt);   o.w = log_add_exp(kLogEps + lat, lbt);
   reinterpret_cast<float4*>(lae)[i] = o;
+}
+
+// the drawn token's row of the next step's denoiser input (see StepParams::emb_*); best_c is warp-uniform
+LDM_DEVINL void embed_next(const StepParams& p, const int b, const int s, const int best_c, const int lane) {
+  if (p.emb_adaln == nullptr) return;
+  const size_t row = static_cast<size_t>(b) * 128 + s;
+  if (p.emb_bf16) embed_token_row<true>(best_c, s, row, p.emb_cat, p.emb_pos, p.emb_adaln, p.emb_x32, p.emb_x16, p.emb_d, lane);
+  else embed_token_row<false>(best_c, s, row, p.emb_cat, p.emb_pos, p.emb_adaln, p.emb_x32, p.emb_x16, p.emb_d, lane);
 }
 
 // predict_start (base.py:127-146) for one token: float64 log-softmax over the C-1 non-MASK classes, MASK = -70, clamp [-70, 0].
@@ -306,6 +319,7 @@ LDM_DEVINL void posterior_token_generic(const StepParams& p, const int token, co
     if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
   }
   if (lane == 0) p.ids_out[token] = best_c;
+  embed_next(p, b, s, best_c, lane);
 }
 
 __global__ void __launch_bounds__(256) posterior_sample_kernel(const StepParams p) {
@@ -518,6 +532,7 @@ __global__ void __launch_bounds__(256) posterior_sample_group_kernel(const StepP
     if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
   }
   if (lane == 0) p.ids_out[token] = best_c;
+  embed_next(p, b, s, best_c, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------

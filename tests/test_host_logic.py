@@ -109,3 +109,53 @@ def test_sampling_struct_mirrors_reference_errors():
     class Cfg:   # attribute-style config (OmegaConf DictConfig behaves like both)
         name, temperature = "random", 0.7
     assert abs(sampling_struct(Cfg()).temperature - 0.7) < 1e-6
+
+
+def test_relation_edge_table_matches_oracle_adjacency():
+    """product-side dense edge table (LdmCond.rel_adj) == the oracle's, built from a PyG-style batch with canvas nodes"""
+    import torch
+    from layoutdm_b200.vocab import relation_edge_table
+    from oracle import layoutdm_oracle as O
+
+    class Batch:
+        pass
+    g = torch.Generator().manual_seed(0)
+    sizes = [26, 2, 9]
+    b = Batch()
+    b.batch = torch.cat([torch.full((n,), i) for i, n in enumerate(sizes)])
+    ei, ea, off = [], [], 0
+    for n in sizes:
+        for i in range(n):
+            for j in range(i + 1, n):
+                if torch.rand(1, generator=g) < 0.3:
+                    ei.append((off + i, off + j)); ea.append(int(torch.randint(1, 1 << 10, (1,), generator=g)))
+        off += n
+    b.edge_index = torch.tensor(ei).t().contiguous()
+    b.edge_attr = torch.tensor(ea)
+    got = relation_edge_table(b, 3, 26)
+    want = O.relation_adjacency(b.edge_index, b.edge_attr, b.batch, 3, 26)
+    assert got.dtype == torch.int32 and torch.equal(got, want) and int((got != 0).sum()) == len(ea)
+    b.edge_index = torch.zeros(2, 0, dtype=torch.long)
+    assert int(relation_edge_table(b, 3, 26).abs().sum()) == 0
+
+
+def test_duplicate_cond_keeps_shared_tables():
+    """one condition, many outputs (task.py:235-248): per-layout tensors repeat, the (C,C) refinement table and the (4,n_bins)
+    relation centres are shared and stay as they are"""
+    import torch
+    from layoutdm_b200.diffusion import duplicate_cond
+    cond = {"seq": torch.zeros(1, 125, dtype=torch.long), "mask": torch.ones(1, 125, dtype=torch.bool), "refine_table": torch.zeros(155, 155),
+            "rel_centers": torch.zeros(4, 32), "rel_adj": torch.zeros(1, 26, 26, dtype=torch.int32), "type": "refinement"}
+    out = duplicate_cond(cond, 4)
+    assert out["seq"].shape == (4, 125) and out["mask"].shape == (4, 125) and out["rel_adj"].shape == (4, 26, 26)
+    assert out["refine_table"].shape == (155, 155) and out["rel_centers"].shape == (4, 32)
+
+
+def test_group_full_ids_cover_the_vocabulary():
+    from layoutdm_b200 import Vocab
+    from layoutdm_b200.vocab import group_full_ids
+    from oracle import layoutdm_oracle as O
+    for name, ov in (("rico25", O.RICO25), ("publaynet", O.PUBLAYNET)):
+        v = Vocab.for_dataset(name)
+        for g in range(5):
+            assert group_full_ids(v, g) == ov.group_full_ids(g)
