@@ -50,7 +50,7 @@ template <bool BF16>
 __global__ void __launch_bounds__(kAttThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64 x 128*/,
                  const __grid_constant__ CUtensorMap map_att /*[M][512], box 64 x 128*/, int n_valid /*125*/, int n_heads /*8*/,
-                 int n_layouts, int ones_col /*58: V column that holds 1.0*/) {
+                 int n_layouts, int ones_col /*58: V column that holds 1.0*/, int rev /*1: walk the items from the last to the first (L2 reuse, see GemmParams::rev)*/) {
   using O = OpT<BF16>;
   extern __shared__ uint8_t att_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -86,7 +86,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
     // ===================== producer: loads two items ahead, stores O (whole warp loops, one elected lane issues) =====================
     {
       auto load = [&](int item, int b) {
-        const int h = item % n_heads, row0 = (item / n_heads) * 128;
+        const int pit = rev ? n_items - 1 - item : item;
+        const int h = pit % n_heads, row0 = (pit / n_heads) * 128;
         uint8_t* buf = smem + b * kAttBuf;
         mbar_arrive_expect_tx(&qkv_full[b], 3 * kAttTile);
         tma_load_2d(buf + kAttOffQ, &map_qkv, &qkv_full[b], h * 64, row0);
@@ -102,7 +103,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
       int hi = 0;
       for (int item = first; item < n_items; item += step, ++hi) {
         const int b = hi & 1;
-        const int h = item % n_heads, row0 = (item / n_heads) * 128;
+        const int pit = rev ? n_items - 1 - item : item;
+        const int h = pit % n_heads, row0 = (pit / n_heads) * 128;
         mbar_wait(o_staged, hi & 1);
         if (elect_one()) {
           tma_store_2d(&map_att, smem_u32(smem + b * kAttBuf + kAttOffO), h * 64, row0);

@@ -61,6 +61,8 @@ struct GemmParams {
   unsigned ln_epoch;
   const int* t_layout;    // EPI_LN + adaln: per-layout timesteps (training-side calls): ln_scale then points at the layer's whole [T][2N]
   int n_layouts;          //   AdaLN table and every (row block, CTA) = layout reloads its (scale, shift) row; nullptr: one timestep for all
+  int rev;                // 1: walk the row blocks from the last to the first.  Consecutive kernels alternate the direction, so a consumer starts with
+                          // the rows its producer wrote last -- the part of the intermediate that is still in the 126 MB L2
   int tile_sched;         // 1: spread single (row block, N tile) tiles over the CTA pairs (small batches); 0: a pair walks all N tiles of a row block
   int dbg;                // bring-up probe (env LDM_GEMM_DEBUG), bit mask: 1 = skip the MMAs, 2 = skip the TMA operand loads, 4 = skip the epilogue body,
                           // 8 = every epilogue store is issued out of bounds (the TMA engine reads the staging tile but writes nothing),
@@ -193,7 +195,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0; uint32_t phase = 0, a_phase = 0;
       for (int o = pair; o < n_outer; o += n_pairs) {
       for (int i = 0; i < n_inner; ++i) {
-        const int sup = p.tile_sched ? o / p.n_tiles : o, n_blk = p.tile_sched ? o % p.n_tiles : i;
+        const int sup0 = p.tile_sched ? o / p.n_tiles : o, n_blk = p.tile_sched ? o % p.n_tiles : i;
+        const int sup = p.rev ? n_super - 1 - sup0 : sup0;
         const int m_blk = 2 * sup + static_cast<int>(cta_rank);
         // weight rows per CTA (the TMA box stays UMMA_N / 2 rows: rows past b_half are unused)
         const int b_half = (EPI == EPI_LN ? (n_blk == 0 ? BN_STORE : UMMA_N) : min(UMMA_N, p.N - n_blk * BN_STORE)) / 2;
@@ -331,7 +334,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if constexpr (EPI != EPI_LN) {
       for (int o = pair; o < n_outer; o += n_pairs)
       for (int i = 0; i < n_inner; ++i) {
-        const int sup = p.tile_sched ? o / p.n_tiles : o, n_blk = p.tile_sched ? o % p.n_tiles : i;
+        const int sup0 = p.tile_sched ? o / p.n_tiles : o, n_blk = p.tile_sched ? o % p.n_tiles : i;
+        const int sup = p.rev ? n_super - 1 - sup0 : sup0;
         const int m_blk = 2 * sup + static_cast<int>(cta_rank);
         const int n0 = n_blk * BN_STORE;
         const int wrow0 = m_blk * kBM + quad * 32;
@@ -396,7 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t lphase = 0;                                   // one phase bit per buffer
       const float inv_n = 1.0f / static_cast<float>(p.N);
       for (int o = pair; o < n_outer; o += n_pairs) {
-        const int sup = o >> 1, n_blk = o & 1;
+        const int sup = p.rev ? n_super - 1 - (o >> 1) : (o >> 1), n_blk = o & 1;
         const int m_blk = 2 * sup + static_cast<int>(cta_rank);
         const int wrow0 = m_blk * kBM + quad * 32;            // first row of this warp
         const int n0 = n_blk * BN_STORE;

@@ -160,6 +160,7 @@ struct LdmHandle {
   // CUDA graph of the whole T-step loop (ldm_sample_loop): captured once per (batch, plan, sampling, conditioning kind) and
   // replayed; everything that changes from call to call lives in device memory (noise key block, staged cond / start ids)
   int use_graph = 1;           // env LDM_GRAPH=0: plain stream launches
+  int sweep = 1;               // env LDM_SWEEP=0: every kernel walks its row blocks in ascending order (no alternating directions)
   int fuse_embed = 1;          // env LDM_FUSE_EMBED=0: the loop launches the embedding kernel in every step instead of fusing it into the previous draw
   cudaStream_t cap_stream = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
@@ -353,6 +354,10 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
   // LN GEMMs: units (row block, column tile) on neighbouring pairs -> an even number of pairs, all of them resident
   const int ln_grid = std::min(2 * np, h->num_sms) & ~3;
   int done = 0;
+  // alternating sweep direction: every kernel walks the row blocks opposite to its predecessor (GemmParams::rev); the embedding /
+  // draw kernels run their blocks in ascending order, so the first GEMM starts from the end.  LDM_SWEEP=0: always ascending
+  int dir = 0;
+  auto next_rev = [&]() { dir ^= 1; return h->sweep ? dir : 0; };
   // test tap: stop after `debug_stop_after` launches
 #define LDM_STAGE_DONE() do { if (h->debug_stop_after && ++done >= h->debug_stop_after) { CK(cudaGetLastError()); return LDM_OK; } } while (0)
   if (!skip_embed) {     // skipped inside the loop: the previous step's draw kernel has already written this step's x32 / x16 rows
@@ -365,7 +370,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
   for (int l = 0; l < L; ++l) {
     {  // QKV projection (+bias, q * 1/sqrt(head_dim))
       GemmParams p{M, kQkvN, d, kQkvN / 256, h->bqkv[l], h->qkv16, kQkvN, 1.0f / sqrtf(static_cast<float>(d / h->desc.n_heads)), 8 * kHeadPad};
-      p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles);
+      p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles); p.rev = next_rev();
       ProfScope ps(h, CAT_QKV, st);
       CK(launch_step(h, gemm_tc_kernel<256, 256, kAresStages, EPI_QKV, BF16, true>, pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, kAresStages, EPI_QKV, true>::kBytes, st, false,
                      h->m_x16, h->m_wqkv[l], h->b_qkv16, h->b_qkv16, h->b_qkv16, h->t_x16, p));
@@ -374,12 +379,12 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     {
       ProfScope ps(h, CAT_ATTN, st);
       CK(launch_step(h, attention_kernel<BF16>, std::min(np * h->desc.n_heads, 2 * h->num_sms), kAttThreads, kAttSmemBytes, st, false,
-                     h->m_qkv16, h->m_att16, h->S, h->desc.n_heads, np, d / h->desc.n_heads));
+                     h->m_qkv16, h->m_att16, h->S, h->desc.n_heads, np, d / h->desc.n_heads, next_rev()));
     }
     LDM_STAGE_DONE();
     {  // out-projection + bias + residual (from the NORMALISED x) -> y32 ; z16 = LayerNorm2(y)   [fused epilogue]
       GemmParams p{M, d, kAttN, 2, h->bo[l], h->z16, d, 1.0f, 0, h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr};
-      p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch;
+      p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch; p.rev = next_rev();
       ProfScope ps(h, CAT_OUTPROJ, st);
       CK(launch_step(h, gemm_tc_kernel<224, 240, 3, EPI_LN, BF16>, ln_grid, kGemmThreads, GemmSmem<240, 3, EPI_LN>::kBytes, st, true,
                      h->m_att16, h->m_wo[l], h->b_z16, h->b_x32, h->b_y32, h->b_y32, p));
@@ -387,7 +392,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     LDM_STAGE_DONE();
     {  // FF1 + ReLU
       GemmParams p{M, ff, d, (ff + 255) / 256, h->b1[l], h->hid16, ff, 1.0f, 0};   // 7 tiles of 256 columns + one of 64
-      p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles);
+      p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles); p.rev = next_rev();
       ProfScope ps(h, CAT_FF1, st);
       CK(launch_step(h, gemm_tc_kernel<256, 256, kAresStages, EPI_RELU, BF16, true>, pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, kAresStages, EPI_RELU, true>::kBytes, st, false,
                      h->m_z16, h->m_w1[l], h->b_hid16, h->b_hid16, h->b_hid16, h->t_z16, p));
@@ -403,7 +408,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       } else {
         p.ln_scale = h->hlnw; p.ln_shift = h->hlnb; p.adaln = 0; p.out32 = nullptr; p.out = h->z16;
       }
-      p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch;
+      p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch; p.rev = next_rev();
       ProfScope ps(h, CAT_FF2, st);
       CK(launch_step(h, gemm_tc_kernel<224, 240, 5, EPI_LN, BF16>, ln_grid, kGemmThreads, GemmSmem<240, 5, EPI_LN>::kBytes, st, true,
                      h->m_hid16, h->m_w2[l], *mo, h->b_y32, h->b_x32, h->b_x32, p));
@@ -412,6 +417,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
   }
   {  // vocabulary head -> fp32 logits
     GemmParams p{M, kLogitLd, d, 1, nullptr, h->logits, kLogitLd, 1.0f, 0};
+    p.rev = next_rev();
     ProfScope ps(h, CAT_HEAD, st);
     CK(launch_step(h, gemm_tc_kernel<160, 160, 5, EPI_F32, BF16>, pair_grid(1), kGemmThreads, GemmSmem<160, 5, EPI_F32>::kBytes, st, false,
                    h->m_z16, h->m_whead, h->b_logits, h->b_logits, h->b_logits, h->b_logits, p));
@@ -559,6 +565,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   if (const char* e = getenv("LDM_PDL")) h->pdl = atoi(e);
   if (const char* e = getenv("LDM_GRAPH")) h->use_graph = atoi(e);
   if (const char* e = getenv("LDM_FUSE_EMBED")) h->fuse_embed = atoi(e);
+  if (const char* e = getenv("LDM_SWEEP")) h->sweep = atoi(e);
 #define TRY(x) do { rc = (x); if (rc) { ldm_destroy(h); return rc; } } while (0)
 
   TRY(dev_upload(h, &h->cat_emb, w->cat_emb, static_cast<size_t>(C) * d));
