@@ -62,6 +62,18 @@ def load_traffic(kernel):
         return None, None
 
 
+def load_precision():
+    """logit error of the 16-bit operand path vs the fp32 oracle at weight scales 1 / 2 / 3, measured on the GPU box by
+    tools/precision_report.py and committed under profiles/ (bench.py itself must not run the oracle outside the CPU legs)"""
+    try:
+        d = json.load(open(os.path.join(REPO, "profiles", "r02c_precision.json")))
+        return {"source": "profiles/r02c_precision.json (tools/precision_report.py: max-abs logit error vs the fp32 oracle, B=32, t in {0, 42, 99})",
+                "rows": [{k: r[k] for k in ("operand_dtype", "weight_scale", "max_abs_logit", "logit_err_vs_fp32", "logit_err_vs_same_rounding", "fp16_headroom_x", "nonfinite")}
+                         for r in d["rows"]]}
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -415,7 +427,7 @@ def run_b200_arm(args, world, rank, local):
                            "global_batch": total, "parallelism": f"dp{world} (batch-sharded replicas, one all-gather of ids)" if world > 1 else "single GPU",
                            "l2": "per-step activation working set (1.9 GB at B=1024) >> 126 MB L2, no explicit flush needed",
                            "operands": f"{args.dtype} tensor-core operands, fp32 accumulate / LayerNorm / softmax / posterior"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "configs": configs}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "configs": configs, "precision": load_precision()}
         emit(json.dumps(line))
 
 
