@@ -62,6 +62,23 @@ def load_traffic(kernel):
         return None, None
 
 
+def kernel_record(k, v, B, tot_ms, peaks):
+    """per-kernel line of the roofline table: achieved tensor rate (algorithmic FLOPs) and HBM rate (algorithmic bytes when every
+    intermediate makes one round trip) against the measured peaks; the kernel's own roofline is the larger of the two fractions"""
+    us = v[0] / v[1] * 1e3
+    r = {"ms_per_pass": round(v[0], 3), "launches": v[1], "us_per_launch": round(us, 1), "share": round(v[0] / tot_ms, 4)}
+    fr = []
+    if k in FLOPS:
+        tf = FLOPS[k] * B / (us * 1e-6) / 1e12
+        r["tflops"] = round(tf, 1); r["tensor_frac"] = round(tf / peaks["sustained"], 3); fr.append(("tensor", r["tensor_frac"]))
+    if k in BYTES:
+        gb = BYTES[k] * B / (us * 1e-6) / 1e9
+        r["hbm_gbs"] = round(gb, 0); r["hbm_frac"] = round(gb / peaks["hbm"], 3); fr.append(("hbm", r["hbm_frac"]))
+    if fr:
+        r["bound"], r["frac"] = max(fr, key=lambda x: x[1])
+    return r
+
+
 def load_precision():
     """logit error of the 16-bit operand path vs the fp32 oracle at weight scales 1 / 2 / 3, measured on the GPU box by
     tools/precision_report.py and committed under profiles/ (bench.py itself must not run the oracle outside the CPU legs)"""
@@ -391,11 +408,7 @@ def run_b200_arm(args, world, rank, local):
                 "frac": achieved / peaks["sustained"], "traffic": traffic, "traffic_unit": "bytes/launch", "traffic_source": traffic_src,
                 "algorithmic_flops_per_launch": FLOPS[dom] * B, "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
                 "share_of_step": dom_ms / tot_prof,
-                "kernels": {k: {"ms_per_pass": round(v[0], 3), "launches": v[1], "share": round(v[0] / tot_prof, 4),
-                                **({"tflops": round(FLOPS[k] * B / (v[0] / v[1] * 1e-3) / 1e12, 1)} if k in FLOPS and v[1] else {}),
-                                **({"hbm_gbs": round(BYTES[k] * B / (v[0] / v[1] * 1e-3) / 1e9, 0),
-                                    "hbm_frac": round(BYTES[k] * B / (v[0] / v[1] * 1e-3) / 1e9 / peaks["hbm"], 3)} if k in BYTES and v[1] else {})}
-                            for k, v in prof.items() if v[1]},
+                "kernels": {k: kernel_record(k, v, B, tot_prof, peaks) for k, v in prof.items() if v[1]},
                 "hbm_peak_gbs": peaks["hbm"],
                 "path_tflops": value / world * T * FLOPS_PER_LAYOUT_STEP / 1e12,
                 "path_frac": value / world * T * FLOPS_PER_LAYOUT_STEP / 1e12 / peaks["sustained"]}
