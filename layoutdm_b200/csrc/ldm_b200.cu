@@ -796,7 +796,7 @@ int ldm_sample_loop(LdmHandle* h, int32_t B, int32_t n_steps, const int32_t* t_m
   key = fnv1a(key, sampling, sizeof(LdmSampling));
   key = fnv1a(key, &h->ws_generation, sizeof(h->ws_generation));
   if (!h->graph_exec || key != h->graph_key) {
-    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    if (h->graph_exec) { CK(cudaStreamSynchronize(st)); cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // no replay of the old plan may still be running
     if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
     const int64_t l0 = h->launches;
     CK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
