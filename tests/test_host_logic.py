@@ -159,3 +159,22 @@ def test_group_full_ids_cover_the_vocabulary():
         v = Vocab.for_dataset(name)
         for g in range(5):
             assert group_full_ids(v, g) == ov.group_full_ids(g)
+
+
+def test_header_is_plain_c():
+    """include/ldm_b200.h is the drop-in boundary: it must compile as C (no C++ / torch types) and declare every symbol the
+    ctypes mirror binds"""
+    import os, re, subprocess, tempfile
+    from layoutdm_b200 import _lib
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(repo, "include", "ldm_b200.h")
+    with tempfile.NamedTemporaryFile("w", suffix=".c", delete=False) as f:
+        f.write('#include "ldm_b200.h"\nint main(void) { LdmCond c = {0}; LdmSampling s = {0}; (void)c; (void)s; return sizeof(LdmModelDesc) > 0 ? 0 : 1; }\n')
+        src = f.name
+    try:
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.dirname(hdr), src])
+    finally:
+        os.unlink(src)
+    text = open(hdr).read()
+    for name in _lib.SIGNATURES:
+        assert re.search(r"\b%s\s*\(" % name, text), f"{name} is bound by the mirror but not declared in the header"
