@@ -165,6 +165,11 @@ int ldm_predict_start(LdmHandle* h, int32_t B, const int64_t* xt_ids_dev, const 
 int ldm_q_posterior(LdmHandle* h, int32_t B, const float* log_x_start_dev, const int64_t* xt_ids_dev, const int32_t* t_dev,
                     float* log_prob_out_dev, void* stream);
 int ldm_q_pred(LdmHandle* h, int32_t B, const float* log_x_start_dev, const int32_t* t_dev, float* log_prob_out_dev, void* stream);
+/* q_pred_one_timestep: log q(x_t | x_{t-1}) with the per-step tables (constrained.py:92-110, vanilla.py:74-88), t in [0, T) */
+int ldm_q_pred_one_timestep(LdmHandle* h, int32_t B, const float* log_x_t_dev, const int32_t* t_dev, float* log_prob_out_dev, void* stream);
+/* log_sample_categorical with train_sampling "gumbel" (constrained.py:208-221): ids = argmax_c(logits + Gumbel noise) on [B][S][C]
+ * logits (-inf = excluded class); noise = Philox stream 2 of the contract, the stream ldm_q_sample draws from. */
+int ldm_gumbel_argmax(LdmHandle* h, int32_t B, const float* logits_dev, uint64_t seed, int64_t b_global0, int64_t* ids_out_dev, void* stream);
 int ldm_vb_terms(LdmHandle* h, int32_t B, const int64_t* x0_ids_dev, const int64_t* xt_ids_dev, const int32_t* t_dev,
                  float mask_weight_mask, float mask_weight_other, float* kl_out_dev, float* decoder_nll_out_dev,
                  float* kl_aux_out_dev, float* log_model_prob_out_dev, int64_t* x0_recon_ids_out_dev,

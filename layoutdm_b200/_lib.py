@@ -56,6 +56,8 @@ SIGNATURES = {
     "ldm_predict_start": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldm_q_posterior": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldm_q_pred": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldm_q_pred_one_timestep": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldm_gumbel_argmax": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]),
     "ldm_vb_terms": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldm_launch_count": (C.c_int64, [C.c_void_p]),

@@ -975,13 +975,32 @@ int ldm_q_posterior(LdmHandle* h, int32_t B, const float* log_x_start, const int
   return LDM_OK;
 }
 
-int ldm_q_pred(LdmHandle* h, int32_t B, const float* log_x_start, const int32_t* t_dev, float* out, void* stream) {
-  if (!h || !log_x_start || !t_dev || !out || B <= 0) return fail(LDM_ERR_INVALID, "bad ldm_q_pred arguments");
+namespace {
+int q_pred_impl(LdmHandle* h, int32_t B, const float* log_x, const int32_t* t_dev, float* out, void* stream, int one_step) {
+  if (!h || !log_x || !t_dev || !out || B <= 0) return fail(LDM_ERR_INVALID, "bad ldm_q_pred arguments");
   CK(cudaSetDevice(h->desc.device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   StepParams p = base_step_params(h, B);
   p.t_layout = t_dev;
-  { ProfScope ps(h, CAT_MISC, st); q_pred_kernel<<<1024, 256, 0, st>>>(p, log_x_start, out); }
+  { ProfScope ps(h, CAT_MISC, st); q_pred_kernel<<<1024, 256, 0, st>>>(p, log_x, out, one_step); }
+  CK(cudaGetLastError());
+  return LDM_OK;
+}
+}  // namespace
+
+int ldm_q_pred(LdmHandle* h, int32_t B, const float* log_x_start, const int32_t* t_dev, float* out, void* stream) {
+  return q_pred_impl(h, B, log_x_start, t_dev, out, stream, 0);
+}
+int ldm_q_pred_one_timestep(LdmHandle* h, int32_t B, const float* log_x_t, const int32_t* t_dev, float* out, void* stream) {
+  return q_pred_impl(h, B, log_x_t, t_dev, out, stream, 1);
+}
+
+int ldm_gumbel_argmax(LdmHandle* h, int32_t B, const float* logits, uint64_t seed, int64_t b_global0, int64_t* ids_out, void* stream) {
+  if (!h || !logits || !ids_out || B <= 0) return fail(LDM_ERR_INVALID, "bad ldm_gumbel_argmax arguments");
+  CK(cudaSetDevice(h->desc.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = (B * h->S * 32 + 255) / 256;
+  { ProfScope ps(h, CAT_MISC, st); gumbel_argmax_kernel<<<blocks, 256, 0, st>>>(logits, reinterpret_cast<long long*>(ids_out), B, h->S, h->C, seed, b_global0); }
   CK(cudaGetLastError());
   return LDM_OK;
 }

@@ -624,7 +624,8 @@ __global__ void row_mean_kernel(const float* __restrict__ in, float* __restrict_
 // q_pred on full-vocabulary (n_layouts, S, C) log tensors: log q(x_t | x_0) for arbitrary log p(x_0) (constrained.py:112-133 per
 // attribute on the partial vocabularies, vanilla.py:90-110); classes outside the token's group stay at log(1e-30) like
 // Converter.p_to_f_log fills them.  t may be -1 (wraps to T, :115).
-__global__ void q_pred_kernel(const StepParams p, const float* __restrict__ lx, float* __restrict__ out) {
+// one_step = 1: q_pred_one_timestep, log q(x_t | x_{t-1}) with the per-step tables (constrained.py:92-110), t in [0, T).
+__global__ void q_pred_kernel(const StepParams p, const float* __restrict__ lx, float* __restrict__ out, const int one_step) {
   const size_t n = static_cast<size_t>(p.n_layouts) * p.S * p.C;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % p.C); const size_t tok = i / p.C; const int s = static_cast<int>(tok % p.S); const int b = static_cast<int>(tok / p.S);
@@ -636,10 +637,45 @@ __global__ void q_pred_kernel(const StepParams p, const float* __restrict__ lx, 
       const int TT = p.T + 1;
       const int t = (__ldg(p.t_layout + b) + TT) % TT;
       const float* tab = p.sched + static_cast<size_t>(g) * 8 * TT;
-      r = (c != p.mask_id) ? log_add_exp(lx[i] + tab[3 * TT + t], tab[4 * TT + t]) : log_add_exp(lx[i] + tab[7 * TT + t], tab[5 * TT + t]);
+      const int ra = one_step ? 0 : 3, rb = one_step ? 1 : 4, rc = one_step ? 2 : 5, r1 = one_step ? 6 : 7;   // (at, bt, ct, 1-ct) vs their cumulative products
+      r = (c != p.mask_id) ? log_add_exp(lx[i] + tab[ra * TT + t], tab[rb * TT + t]) : log_add_exp(lx[i] + tab[r1 * TT + t], tab[rc * TT + t]);
     }
     out[i] = r;
   }
+}
+
+// log_sample_categorical with train_sampling = "gumbel" (constrained.py:208-221): ids = argmax_c(logits_c + Gumbel noise) on
+// (n_layouts, S, C) logits; classes the caller wants excluded carry -inf.  Noise = Philox stream 2, the stream q_sample_kernel draws
+// from, so log_sample_categorical(q_pred(log_onehot(x0), t)) reproduces ldm_q_sample bit for bit.  One warp per token.
+__global__ void __launch_bounds__(256) gumbel_argmax_kernel(const float* __restrict__ logits, long long* __restrict__ ids_out, int n_layouts, int S, int C,
+                                                            unsigned long long seed, long long b_global0) {
+  const int token = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (token >= n_layouts * S) return;
+  const int b = token / S, s = token % S;
+  const unsigned long long tok = (static_cast<unsigned long long>(b_global0) + b) * static_cast<unsigned long long>(S) + s;
+  const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  const uint32_t tok_lo = static_cast<uint32_t>(tok), tok_hi = static_cast<uint32_t>(tok >> 32);
+  const uint4 ga = philox4x32_10(make_uint4(static_cast<uint32_t>(lane), 2u << 24, tok_lo, tok_hi), key);
+  const uint4 gb = philox4x32_10(make_uint4(32u + (static_cast<uint32_t>(lane) >> 2), 2u << 24, tok_lo, tok_hi), key);
+  const uint32_t gw[5] = {ga.x, ga.y, ga.z, ga.w, (lane & 3) == 0 ? gb.x : (lane & 3) == 1 ? gb.y : (lane & 3) == 2 ? gb.z : gb.w};
+  float best = -INFINITY; int best_c = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int c = j < 4 ? 4 * lane + j : 128 + lane;
+    if (c >= C) continue;
+    const float l = logits[static_cast<size_t>(token) * C + c];
+    if (!(l > -INFINITY)) continue;
+    const float u = u01_from_bits(gw[j]);
+    const float score = l + (-logf(-logf(u + 1e-30f) + 1e-30f));
+    if (score > best || (score == best && c < best_c)) { best = score; best_c = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+    if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+  }
+  if (lane == 0) ids_out[token] = best_c;
 }
 
 // ---------------------------------------------------------------------------------------------------------

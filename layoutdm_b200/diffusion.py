@@ -204,6 +204,44 @@ class FusedMaskAndReplaceDiffusion:
         out = self.engine.q_pred(full, t)
         return out[:, g::v.n_attr][..., ids].permute(0, 2, 1).contiguous()
 
+    def _partial_to_full(self, x: torch.Tensor, key: Optional[str], fill: float):
+        """(B, K_key, S/5) tensor on attribute `key`'s partial vocabulary -> ((B, S, C) full tensor with `fill` elsewhere, group index, ids)"""
+        v = self.vocab
+        g = self._key_index(key)
+        ids = torch.tensor(group_full_ids(v, g), device=self.device)
+        B, K, Sg = x.shape
+        assert K == ids.numel() and Sg == v.n_elem
+        full = torch.full((B, v.S, v.C), fill, device=self.device)
+        full[:, g::v.n_attr, ids] = x.to(self.device).permute(0, 2, 1)
+        return full, g, ids
+
+    def q_pred_one_timestep(self, log_x_t: torch.Tensor, t: torch.Tensor, key: Optional[str] = None) -> torch.Tensor:
+        """constrained.py:92-110 / vanilla.py:74-88: log q(x_t|x_{t-1}); partial vocabulary (B, K_key, S/5) with `key`, else (B,C,S)"""
+        if self.engine.q_type != "constrained" or key is None:
+            return self.engine.q_pred_one_timestep(log_x_t.permute(0, 2, 1), t).permute(0, 2, 1).contiguous()
+        full, g, ids = self._partial_to_full(log_x_t, key, -69.07755278982137)
+        out = self.engine.q_pred_one_timestep(full, t)
+        return out[:, g::self.vocab.n_attr][..., ids].permute(0, 2, 1).contiguous()
+
+    def log_sample_categorical(self, logits: torch.Tensor, key: Optional[str] = None, seed: Optional[int] = None) -> torch.Tensor:
+        """constrained.py:208-221 (train_sampling "gumbel"): log one-hot of argmax(logits + Gumbel noise) along the class dim"""
+        seed = self._new_seed() if seed is None else seed
+        v = self.vocab
+        if self.engine.q_type != "constrained" or key is None:
+            return index_to_log_onehot(self.engine.gumbel_argmax(logits.permute(0, 2, 1), seed), v.C)
+        full, g, ids = self._partial_to_full(logits, key, float("-inf"))
+        full[:, [a for a in range(v.S) if a % v.n_attr != g]] = 0.0        # other attributes' positions: any finite row (their draw is discarded)
+        xt = self.engine.gumbel_argmax(full, seed)[:, g::v.n_attr]
+        return index_to_log_onehot((xt[..., None] == ids).long().argmax(-1), ids.numel())
+
+    def sample_logits(self, logits: torch.Tensor, sampling_cfg, seed: Optional[int] = None) -> torch.Tensor:
+        """helpers/sampling.py:81-130 `sample(logits, sampling_cfg)`: (B,C,S) logits -> (B,1,S) ids"""
+        B = logits.shape[0]
+        dummy = torch.zeros(B, self.vocab.S, dtype=torch.long, device=self.device)
+        out, _, _ = self.engine.step(dummy, 0, 0, sampling_cfg, None, self._new_seed() if seed is None else seed, 0,
+                                     logprob_in=logits.to(self.device).permute(0, 2, 1))
+        return out[:, None, :]
+
     def q_sample(self, log_x_start: torch.Tensor, t: torch.Tensor, key: Optional[str] = None, seed: Optional[int] = None) -> torch.Tensor:
         """constrained.py:223-230: x_t ~ q(x_t|x_0) for attribute `key` (log one-hot in, log one-hot out, partial vocabulary)"""
         v = self.vocab

@@ -254,6 +254,24 @@ class Engine:
         _lib.check(self.lib.ldm_q_pred(self._h, B, _ptr(lx), _ptr(t32), _ptr(out), self._stream()))
         return out
 
+    def q_pred_one_timestep(self, log_x_t: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """constrained.py:92-110 on the full vocabulary: log_x_t (B,S,C), t (B,) in [0, T) -> log q(x_t|x_{t-1}) (B,S,C)"""
+        B = log_x_t.shape[0]
+        lx = log_x_t.to(self.device, torch.float32).contiguous()
+        t32 = self._t32(t, B)
+        out = torch.empty_like(lx)
+        _lib.check(self.lib.ldm_q_pred_one_timestep(self._h, B, _ptr(lx), _ptr(t32), _ptr(out), self._stream()))
+        return out
+
+    def gumbel_argmax(self, logits: torch.Tensor, seed: int = 0, b_global0: int = 0) -> torch.Tensor:
+        """log_sample_categorical, train_sampling "gumbel" (constrained.py:208-221): logits (B,S,C) -> ids (B,S)"""
+        B = logits.shape[0]
+        lg = logits.to(self.device, torch.float32).contiguous()
+        assert lg.shape == (B, self.vocab.S, self.vocab.C)
+        out = torch.empty(B, self.vocab.S, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.ldm_gumbel_argmax(self._h, B, _ptr(lg), C.c_uint64(seed), C.c_int64(b_global0), _ptr(out), self._stream()))
+        return out
+
     def vb_terms(self, x0: torch.Tensor, xt: torch.Tensor, t: torch.Tensor, mask_weight=(1.0, 1.0), want_aux: bool = True,
                  want_log_model_prob: bool = False, want_recon_ids: bool = False) -> Dict[str, torch.Tensor]:
         """the per-layout loss terms of `forward` (constrained.py:262-333) after x_t has been drawn; tensors on the GPU"""

@@ -356,6 +356,33 @@ def q_pred_full(log_x_start: torch.Tensor, t: torch.Tensor, T: int, vocab: Vocab
     return out
 
 
+def q_pred_one_timestep_full(log_x_t: torch.Tensor, t: torch.Tensor, T: int, vocab: VocabSpec, scheds: List[Dict[str, torch.Tensor]],
+                             q_type: str = "constrained") -> torch.Tensor:
+    """q_pred_one_timestep (constrained.py:92-110, vanilla.py:74-88) on full-vocabulary (B,S,C) log tensors, t (B,) in [0, T)"""
+    f = lambda tab, name: tab[name][t].view(-1, 1, 1)
+
+    def group(lx, tab):
+        return torch.cat([_log_add_exp(lx[..., :-1] + f(tab, "log_at"), f(tab, "log_bt")),
+                          _log_add_exp(lx[..., -1:] + f(tab, "log_1_min_ct"), f(tab, "log_ct"))], dim=-1)
+    if q_type == "vanilla":
+        return group(log_x_t, scheds[0])
+    out = torch.full_like(log_x_t, LOG_EPS)
+    S = log_x_t.shape[1]
+    for g in range(vocab.n_attr):
+        idx = torch.tensor(vocab.group_full_ids(g))
+        sl = slice(g, S, vocab.n_attr)
+        tmp = out[:, sl]
+        tmp[..., idx] = group(log_x_t[:, sl][..., idx], scheds[g])
+        out[:, sl] = tmp
+    return out
+
+
+def gumbel_argmax(logits: torch.Tensor, u: np.ndarray) -> torch.Tensor:
+    """log_sample_categorical, train_sampling "gumbel" (constrained.py:208-215): argmax(logits - log(-log(u + 1e-30) + 1e-30))"""
+    g = -torch.log(-torch.log(torch.from_numpy(u) + 1e-30) + 1e-30)
+    return (g + logits).argmax(dim=-1)
+
+
 def vb_terms(logits: torch.Tensor, x0: torch.Tensor, xt: torch.Tensor, t: torch.Tensor, T: int, vocab: VocabSpec,
              scheds: List[Dict[str, torch.Tensor]], q_type: str = "constrained", mask_weight=(1.0, 1.0)) -> Dict[str, torch.Tensor]:
     """The loss terms `forward` derives from the denoiser logits at x_t (constrained.py:262-325, vanilla.py:196-236), per layout:

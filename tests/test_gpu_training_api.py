@@ -47,6 +47,15 @@ def test_q_posterior_and_q_pred_match_oracle(q_type):
     tq = t.clone(); tq[0] = -1
     gp = eng.q_pred(lx.cuda(), tq.cuda()).cpu()
     assert (gp - O.q_pred_full(lx, tq, spec.T, vo, scheds, q_type)).abs().max() < TOL
+    g1 = eng.q_pred_one_timestep(lx.cuda(), t.cuda()).cpu()
+    assert (g1 - O.q_pred_one_timestep_full(lx, t, spec.T, vo, scheds, q_type)).abs().max() < TOL
+    # log_sample_categorical (gumbel argmax): bit-exact vs the oracle under the shared noise, and == ldm_q_sample when fed q_pred(one-hot x0)
+    ids = eng.gumbel_argmax(lx.cuda(), seed=7).cpu()
+    assert torch.equal(ids, O.gumbel_argmax(lx, O.uniforms(7, 0, 2, 0, B, vo.S, vo.C)))
+    if q_type == "constrained":
+        qp = eng.q_pred(one.cuda(), t.cuda())
+        qp = torch.where(qp > O.LOG_EPS + 1e-3, qp, torch.full_like(qp, float("-inf")))      # classes outside the token's group are impossible
+        assert torch.equal(eng.gumbel_argmax(qp, seed=21), eng.q_sample(x0.cuda(), t.cuda(), seed=21))
 
 
 @pytest.mark.parametrize("q_type,B", [("constrained", 18), ("constrained", 301), ("vanilla", 9)])
@@ -107,6 +116,14 @@ def test_reference_class_api_training_side():
         one = torch.log(torch.nn.functional.one_hot(torch.randint(0, len(idx) - 2, (B, 25), generator=g), len(idx)).permute(0, 2, 1).float().clamp(min=1e-30))
         xs = core.q_sample(one.cuda(), t.cuda(), key, seed=3)
         assert xs.shape == one.shape and torch.allclose(xs.exp().sum(1), torch.ones(B, 25, device=xs.device), atol=1e-6)
+        one_t = core.q_pred_one_timestep(part.cuda(), t.cuda(), key).cpu()
+        want_1 = O.q_pred_one_timestep_full(full, t, 100, vo, scheds)[:, a::5][..., idx].permute(0, 2, 1)
+        assert (one_t - want_1).abs().max() < TOL
+        ls = core.log_sample_categorical(part.cuda(), key, seed=5)
+        assert ls.shape == part.shape and torch.allclose(ls.exp().sum(1), torch.ones(B, 25, device=ls.device), atol=1e-6)
+    lg = torch.randn(B, vo.C, vo.S, generator=g)
+    drawn = core.sample_logits(lg.cuda(), {"name": "deterministic"})
+    assert drawn.shape == (B, 1, vo.S) and torch.equal(drawn[:, 0].cpu(), lg.argmax(1))
     pt = torch.full((B,), 0.01)
     outputs, losses = core.forward(x0.cuda(), is_train=True, t=t, pt=pt, seed=11)
     assert outputs["probs"].shape == (B, vo.C, vo.S) and torch.isfinite(losses["kl_loss"]) and torch.isfinite(losses["aux_loss"])

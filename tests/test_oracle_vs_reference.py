@@ -122,6 +122,30 @@ def test_training_side_api_matches_reference(q_type):
         with torch.no_grad():
             w = core.q_pred(lx.permute(0, 2, 1), tq)
         assert (full.permute(0, 2, 1) - w).abs().max() < 1e-5
+    # 2b. q_pred_one_timestep and log_sample_categorical (gumbel) with the noise injected through torch.rand_like
+    t1 = torch.tensor([0, 1, 50, 99, 37, 5, 98])
+    one = O.q_pred_one_timestep_full(lx, t1, 100, vocab, scheds, q_type)
+    u_all = O.uniforms(9, 0, 2, 0, B, S, C)
+    if q_type == "constrained":
+        for a, key in enumerate("cxywh"):
+            idx = torch.tensor(vocab.group_full_ids(a))
+            part = lx[:, a::5][..., idx].permute(0, 2, 1)
+            with torch.no_grad():
+                w = core.q_pred_one_timestep(part, t1, key)
+            assert (one[:, a::5][..., idx].permute(0, 2, 1) - w).abs().max() < 1e-5
+            u_part = torch.from_numpy(u_all)[:, a::5][..., idx].permute(0, 2, 1).contiguous()
+            orig = torch.rand_like
+            torch.rand_like = lambda x, **kw: u_part
+            try:
+                got_ref = core.log_sample_categorical(part, key).argmax(1)
+            finally:
+                torch.rand_like = orig
+            want_o = O.gumbel_argmax(part.permute(0, 2, 1), u_part.permute(0, 2, 1).numpy())
+            assert torch.equal(got_ref, want_o)
+    else:
+        with torch.no_grad():
+            w = core.q_pred_one_timestep(lx.permute(0, 2, 1), t1)
+        assert (one.permute(0, 2, 1) - w).abs().max() < 1e-5
     # 3. forward: inject (t, pt) and the corruption so that the reference sees the same x_t
     pt = torch.full((B,), 1.0 / 100)
     core.sample_time = lambda b, device, method="uniform": (t, pt)
