@@ -347,3 +347,25 @@ def test_make_cond_kernel_matches_oracle(cond_type):
         assert torch.equal(ids[got["mask"]], got["seq"][got["mask"]])
     with pytest.raises(NotImplementedError):
         eng.cond_from_layouts(label, bbox, mask, "partial")
+
+
+def test_loop_edge_plans_and_replay():
+    """shortest plans (T_eval = 1, 2), alternating batch sizes on one handle (the captured graph is re-recorded when the plan or the
+    batch changes and replayed otherwise), and replay == first run"""
+    from layoutdm_b200 import timestep_plan
+    fx = Fixture("rico25_uncond_random")
+    eng = engine_for(fx)
+    cfg = {"name": "random", "temperature": 1.0}
+    for T_eval in (1, 2):
+        plan = timestep_plan(fx.spec.T, T_eval)
+        ids = eng.sample_loop(3, plan, cfg, seed=1)
+        assert plan[-1][0] == 0 and (ids != fx.vocab.mask_id).all() and int(ids.max()) < fx.vocab.C
+    plan = timestep_plan(fx.spec.T, 7)
+    ref = {}
+    for B in (3, 5, 3, 5, 3):
+        ids = eng.sample_loop(B, plan, cfg, seed=11)
+        assert B not in ref or torch.equal(ids, ref[B])       # same key -> same ids, whether the graph was re-recorded or replayed
+        ref.setdefault(B, ids.clone())
+    assert torch.equal(ref[5][:3], ref[3])                    # noise is keyed by the layout index, not by the batch size
+    ids2, trace = eng.sample_loop(3, plan, cfg, seed=11, trace=True)   # plain (non-graph) path with the trace
+    assert torch.equal(ids2, ref[3])
