@@ -61,12 +61,16 @@ struct GemmParams {
   unsigned ln_epoch;
   const int* t_layout;    // EPI_LN + adaln: per-layout timesteps (training-side calls): ln_scale then points at the layer's whole [T][2N]
   int n_layouts;          //   AdaLN table and every (row block, CTA) = layout reloads its (scale, shift) row; nullptr: one timestep for all
+  int store_evict_last;   // 1: the epilogue's TMA stores carry an L2 evict_last hint (QKV / FF1: the freshly written qkv16 / hid16 rows stay in L2 for the
+                          // consumer that -- with alternating sweep directions -- reads them first; measured FF1 198 -> 187 us, QKV 160 -> 156, attention 95 -> 92)
   int rev;                // 1: walk the row blocks from the last to the first.  Consecutive kernels alternate the direction, so a consumer starts with
                           // the rows its producer wrote last -- the part of the intermediate that is still in the 126 MB L2
   int tile_sched;         // 1: spread single (row block, N tile) tiles over the CTA pairs (small batches); 0: a pair walks all N tiles of a row block
   int dbg;                // bring-up probe (env LDM_GEMM_DEBUG), bit mask: 1 = skip the MMAs, 2 = skip the TMA operand loads, 4 = skip the epilogue body,
                           // 8 = every epilogue store is issued out of bounds (the TMA engine reads the staging tile but writes nothing),
-                          // 16 = every epilogue store lands in the first 256 rows (an L2-resident window: no HBM write stream); results are garbage
+                          // 16 = every epilogue store lands in the first 8192 rows (an L2-resident window: no HBM write stream); results are garbage.
+                          // L2 eviction-priority experiments (results stay correct): 32 = epilogue stores evict_first, 128 = epilogue stores evict_last,
+                          // 64 = weight tiles evict_last
 };
 
 #ifndef LDM_ARES_STORE_BUFS
@@ -224,7 +228,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             else {
               mbar_arrive_expect_tx_cluster(lead_full, SM::kStageBytes);
               if constexpr (!ARES) tma_load_2d_2cta(sa, &map_a, lead_full, kb * kBK, m_blk * kBM);
-              tma_load_2d_2cta(sa + (ARES ? 0 : kATileBytes), &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * b_half);
+              if (p.dbg & 64) tma_load_2d_2cta_hint(sa + (ARES ? 0 : kATileBytes), &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * b_half, l2_policy_evict_last());
+              else tma_load_2d_2cta(sa + (ARES ? 0 : kATileBytes), &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * b_half);
             }
           }
           __syncwarp();
@@ -297,6 +302,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int st_or = (p.dbg & 8) ? 0x40000000 : 0, st_and = (p.dbg & 16) ? 8191 : 0x7fffffff;   // store-stream probes (see GemmParams::dbg)
     // Staging blocks are recycled per block, not per warp: every TMA store is its own bulk group, groups retire in order, so before a
     // block is rewritten only the groups up to its previous store have to have left shared memory -- the newer ones stay in flight.
+    const bool st_hint = (p.dbg & (32 | 128)) != 0 || p.store_evict_last != 0;
+    const uint64_t st_policy = (p.dbg & 32) ? l2_policy_evict_first() : l2_policy_evict_last();
     int n_groups = 0, last_g16[2] = {-1000, -1000}, last_g32 = -1000;
     uint32_t buf16 = 0;                        // which of the kStoreBufs 16-bit blocks the next store uses
     // stage one 32 x 32 block (this warp's rows, 32 columns) and hand it to the TMA engine
@@ -310,7 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { tma_store_2d(m, s32, col, row0); bulk_commit(); }
+      if (lane == 0) { if (st_hint) tma_store_2d_hint(m, s32, col, row0, st_policy); else tma_store_2d(m, s32, col, row0); bulk_commit(); }
       last_g32 = n_groups++;
     };
     auto store_16 = [&](const CUtensorMap* m, const float* v, int col, int row0) {
@@ -325,7 +332,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                           O::pack(v[8 * c + 4], v[8 * c + 5]), O::pack(v[8 * c + 6], v[8 * c + 7])));
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { tma_store_2d(m, sb, col, row0); bulk_commit(); }
+      if (lane == 0) { if (st_hint) tma_store_2d_hint(m, sb, col, row0, st_policy); else tma_store_2d(m, sb, col, row0); bulk_commit(); }
       last_g16[buf16] = n_groups++;
       if (SM::kStoreBufs > 1) buf16 ^= 1u;
     };

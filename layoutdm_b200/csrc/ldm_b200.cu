@@ -161,6 +161,7 @@ struct LdmHandle {
   // replayed; everything that changes from call to call lives in device memory (noise key block, staged cond / start ids)
   int use_graph = 1;           // env LDM_GRAPH=0: plain stream launches
   int sweep = 1;               // env LDM_SWEEP=0: every kernel walks its row blocks in ascending order (no alternating directions)
+  int l2_hint = 1;             // env LDM_L2_HINT=0: no evict_last hint on the QKV / FF1 epilogue stores
   int fuse_embed = 1;          // env LDM_FUSE_EMBED=0: the loop launches the embedding kernel in every step instead of fusing it into the previous draw
   cudaStream_t cap_stream = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
@@ -370,7 +371,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
   for (int l = 0; l < L; ++l) {
     {  // QKV projection (+bias, q * 1/sqrt(head_dim))
       GemmParams p{M, kQkvN, d, kQkvN / 256, h->bqkv[l], h->qkv16, kQkvN, 1.0f / sqrtf(static_cast<float>(d / h->desc.n_heads)), 8 * kHeadPad};
-      p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles); p.rev = next_rev();
+      p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles); p.rev = next_rev(); p.store_evict_last = h->l2_hint;
       ProfScope ps(h, CAT_QKV, st);
       CK(launch_step(h, gemm_tc_kernel<256, 256, kAresStages, EPI_QKV, BF16, true>, pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, kAresStages, EPI_QKV, true>::kBytes, st, false,
                      h->m_x16, h->m_wqkv[l], h->b_qkv16, h->b_qkv16, h->b_qkv16, h->t_x16, p));
@@ -392,7 +393,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     LDM_STAGE_DONE();
     {  // FF1 + ReLU
       GemmParams p{M, ff, d, (ff + 255) / 256, h->b1[l], h->hid16, ff, 1.0f, 0};   // 7 tiles of 256 columns + one of 64
-      p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles); p.rev = next_rev();
+      p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles); p.rev = next_rev(); p.store_evict_last = h->l2_hint;
       ProfScope ps(h, CAT_FF1, st);
       CK(launch_step(h, gemm_tc_kernel<256, 256, kAresStages, EPI_RELU, BF16, true>, pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, kAresStages, EPI_RELU, true>::kBytes, st, false,
                      h->m_z16, h->m_w1[l], h->b_hid16, h->b_hid16, h->b_hid16, h->t_z16, p));
@@ -566,6 +567,7 @@ int ldm_create(const LdmModelDesc* desc, const LdmWeights* w, LdmHandle** out) {
   if (const char* e = getenv("LDM_GRAPH")) h->use_graph = atoi(e);
   if (const char* e = getenv("LDM_FUSE_EMBED")) h->fuse_embed = atoi(e);
   if (const char* e = getenv("LDM_SWEEP")) h->sweep = atoi(e);
+  if (const char* e = getenv("LDM_L2_HINT")) h->l2_hint = atoi(e);
 #define TRY(x) do { rc = (x); if (rc) { ldm_destroy(h); return rc; } } while (0)
 
   TRY(dev_upload(h, &h->cat_emb, w->cat_emb, static_cast<size_t>(C) * d));
