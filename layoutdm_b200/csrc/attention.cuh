@@ -50,7 +50,8 @@ template <bool BF16>
 __global__ void __launch_bounds__(kAttThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64 x 128*/,
                  const __grid_constant__ CUtensorMap map_att /*[M][512], box 64 x 128*/, int n_valid /*125*/, int n_heads /*8*/,
-                 int n_layouts, int ones_col /*58: V column that holds 1.0*/, int rev /*1: walk the items from the last to the first (L2 reuse, see GemmParams::rev)*/) {
+                 int n_layouts, int ones_col /*58: V column that holds 1.0*/, int rev /*1: walk the items from the last to the first (L2 reuse, see GemmParams::rev)*/,
+                 int store_evict_last /*bit 0: L2 evict_last hint on the O stores (the out-projection reads them next); bit 1: evict_first on the Q / K / V loads (dead afterwards)*/) {
   using O = OpT<BF16>;
   extern __shared__ uint8_t att_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -90,9 +91,16 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
         const int h = pit % n_heads, row0 = (pit / n_heads) * 128;
         uint8_t* buf = smem + b * kAttBuf;
         mbar_arrive_expect_tx(&qkv_full[b], 3 * kAttTile);
-        tma_load_2d(buf + kAttOffQ, &map_qkv, &qkv_full[b], h * 64, row0);
-        tma_load_2d(buf + kAttOffK, &map_qkv, &qkv_full[b], n_heads * 64 + h * 64, row0);
-        tma_load_2d(buf + kAttOffV, &map_qkv, &qkv_full[b], 2 * n_heads * 64 + h * 64, row0);
+        if (store_evict_last & 2) {
+          const uint64_t pol = l2_policy_evict_first();
+          tma_load_2d_hint(buf + kAttOffQ, &map_qkv, &qkv_full[b], h * 64, row0, pol);
+          tma_load_2d_hint(buf + kAttOffK, &map_qkv, &qkv_full[b], n_heads * 64 + h * 64, row0, pol);
+          tma_load_2d_hint(buf + kAttOffV, &map_qkv, &qkv_full[b], 2 * n_heads * 64 + h * 64, row0, pol);
+        } else {
+          tma_load_2d(buf + kAttOffQ, &map_qkv, &qkv_full[b], h * 64, row0);
+          tma_load_2d(buf + kAttOffK, &map_qkv, &qkv_full[b], n_heads * 64 + h * 64, row0);
+          tma_load_2d(buf + kAttOffV, &map_qkv, &qkv_full[b], 2 * n_heads * 64 + h * 64, row0);
+        }
       };
       const int first = blockIdx.x;
       if (elect_one()) {
@@ -107,7 +115,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map_qkv /*[M][1536], box 64
         const int h = pit % n_heads, row0 = (pit / n_heads) * 128;
         mbar_wait(o_staged, hi & 1);
         if (elect_one()) {
-          tma_store_2d(&map_att, smem_u32(smem + b * kAttBuf + kAttOffO), h * 64, row0);
+          if (store_evict_last & 1) tma_store_2d_hint(&map_att, smem_u32(smem + b * kAttBuf + kAttOffO), h * 64, row0, l2_policy_evict_last());
+          else tma_store_2d(&map_att, smem_u32(smem + b * kAttBuf + kAttOffO), h * 64, row0);
           bulk_commit();
           if (item + 2 * step < n_items) {
             bulk_wait_read0();                                   // the store has read the staging tile: the buffer is free

@@ -63,6 +63,7 @@ struct GemmParams {
   int n_layouts;          //   AdaLN table and every (row block, CTA) = layout reloads its (scale, shift) row; nullptr: one timestep for all
   int store_evict_last;   // 1: the epilogue's TMA stores carry an L2 evict_last hint (QKV / FF1: the freshly written qkv16 / hid16 rows stay in L2 for the
                           // consumer that -- with alternating sweep directions -- reads them first; measured FF1 198 -> 187 us, QKV 160 -> 156, attention 95 -> 92)
+  int load_evict_first;   // bit 0: the A operand tiles, bit 1: the LN residual blocks are loaded with an L2 evict_first hint (read once, dead afterwards)
   int rev;                // 1: walk the row blocks from the last to the first.  Consecutive kernels alternate the direction, so a consumer starts with
                           // the rows its producer wrote last -- the part of the intermediate that is still in the 126 MB L2
   int tile_sched;         // 1: spread single (row block, N tile) tiles over the CTA pairs (small batches); 0: a pair walks all N tiles of a row block
@@ -214,7 +215,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 else {
                   const bool tail = (kb == num_kb - 1) && (p.K & (kBK - 1)) != 0;   // K % 64 == 16 (checked by the host)
                   mbar_arrive_expect_tx_cluster(lead_afull, tail ? SM::kATailBytes : kATileBytes);
-                  tma_load_2d_2cta(smem + kb * kATileBytes, tail ? &map_out32 : &map_a, lead_afull, kb * kBK, m_blk * kBM);
+                  if (p.load_evict_first & 1) tma_load_2d_2cta_hint(smem + kb * kATileBytes, tail ? &map_out32 : &map_a, lead_afull, kb * kBK, m_blk * kBM, l2_policy_evict_first());
+                  else tma_load_2d_2cta(smem + kb * kATileBytes, tail ? &map_out32 : &map_a, lead_afull, kb * kBK, m_blk * kBM);
                 }
               }
               __syncwarp();
@@ -227,7 +229,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (p.dbg & 2) { mbar_arrive_cluster(lead_full); }
             else {
               mbar_arrive_expect_tx_cluster(lead_full, SM::kStageBytes);
-              if constexpr (!ARES) tma_load_2d_2cta(sa, &map_a, lead_full, kb * kBK, m_blk * kBM);
+              if constexpr (!ARES) {
+                if (p.load_evict_first & 1) tma_load_2d_2cta_hint(sa, &map_a, lead_full, kb * kBK, m_blk * kBM, l2_policy_evict_first());
+                else tma_load_2d_2cta(sa, &map_a, lead_full, kb * kBK, m_blk * kBM);
+              }
               if (p.dbg & 64) tma_load_2d_2cta_hint(sa + (ARES ? 0 : kATileBytes), &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * b_half, l2_policy_evict_last());
               else tma_load_2d_2cta(sa + (ARES ? 0 : kATileBytes), &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * b_half);
             }
@@ -302,7 +307,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int st_or = (p.dbg & 8) ? 0x40000000 : 0, st_and = (p.dbg & 16) ? 8191 : 0x7fffffff;   // store-stream probes (see GemmParams::dbg)
     // Staging blocks are recycled per block, not per warp: every TMA store is its own bulk group, groups retire in order, so before a
     // block is rewritten only the groups up to its previous store have to have left shared memory -- the newer ones stay in flight.
-    const bool st_hint = (p.dbg & (32 | 128)) != 0 || p.store_evict_last != 0;
+    const bool st_hint16 = (p.dbg & (32 | 128)) != 0 || (p.store_evict_last & 1) != 0;     // bit 0: 16-bit stores, bit 1: fp32 stores
+    const bool st_hint32 = (p.dbg & (32 | 128)) != 0 || (p.store_evict_last & 2) != 0;
     const uint64_t st_policy = (p.dbg & 32) ? l2_policy_evict_first() : l2_policy_evict_last();
     int n_groups = 0, last_g16[2] = {-1000, -1000}, last_g32 = -1000;
     uint32_t buf16 = 0;                        // which of the kStoreBufs 16-bit blocks the next store uses
@@ -317,7 +323,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { if (st_hint) tma_store_2d_hint(m, s32, col, row0, st_policy); else tma_store_2d(m, s32, col, row0); bulk_commit(); }
+      if (lane == 0) { if (st_hint32) tma_store_2d_hint(m, s32, col, row0, st_policy); else tma_store_2d(m, s32, col, row0); bulk_commit(); }
       last_g32 = n_groups++;
     };
     auto store_16 = [&](const CUtensorMap* m, const float* v, int col, int row0) {
@@ -332,7 +338,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                           O::pack(v[8 * c + 4], v[8 * c + 5]), O::pack(v[8 * c + 6], v[8 * c + 7])));
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { if (st_hint) tma_store_2d_hint(m, sb, col, row0, st_policy); else tma_store_2d(m, sb, col, row0); bulk_commit(); }
+      if (lane == 0) { if (st_hint16) tma_store_2d_hint(m, sb, col, row0, st_policy); else tma_store_2d(m, sb, col, row0); bulk_commit(); }
       last_g16[buf16] = n_groups++;
       if (SM::kStoreBufs > 1) buf16 ^= 1u;
     };
@@ -432,7 +438,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (lane == 0 && c < ce) {
               const int b = (c - c_begin) % n_lbuf;
               mbar_arrive_expect_tx(&lbar[b], 4096);
-              tma_load_2d(wbuf_ptr + lbuf_off[b], &map_resid, &lbar[b], n0 + c * 32, wrow0);
+              if (p.load_evict_first & 2) tma_load_2d_hint(wbuf_ptr + lbuf_off[b], &map_resid, &lbar[b], n0 + c * 32, wrow0, l2_policy_evict_first());
+              else tma_load_2d(wbuf_ptr + lbuf_off[b], &map_resid, &lbar[b], n0 + c * 32, wrow0);
             }
           };
           if ((SM::kLnCompact || (!SM::kLnExtraBuf && n_lbuf == 2)) && lane == 0) bulk_wait_read0();   // the previous unit's stores have left the staging blocks the loads reuse
