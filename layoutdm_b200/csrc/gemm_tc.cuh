@@ -63,7 +63,8 @@ struct GemmParams {
   int n_layouts;          //   AdaLN table and every (row block, CTA) = layout reloads its (scale, shift) row; nullptr: one timestep for all
   int store_evict_last;   // 1: the epilogue's TMA stores carry an L2 evict_last hint (QKV / FF1: the freshly written qkv16 / hid16 rows stay in L2 for the
                           // consumer that -- with alternating sweep directions -- reads them first; measured FF1 198 -> 187 us, QKV 160 -> 156, attention 95 -> 92)
-  int load_evict_first;   // bit 0: the A operand tiles, bit 1: the LN residual blocks are loaded with an L2 evict_first hint (read once, dead afterwards)
+  int load_evict_first;   // bit 0: the A operand tiles, bit 1: the LN residual blocks are loaded with an L2 evict_first hint (read once, dead afterwards);
+                          // bit 2: the weight tiles are loaded with an evict_last hint
   int rev;                // 1: walk the row blocks from the last to the first.  Consecutive kernels alternate the direction, so a consumer starts with
                           // the rows its producer wrote last -- the part of the intermediate that is still in the 126 MB L2
   int tile_sched;         // 1: spread single (row block, N tile) tiles over the CTA pairs (small batches); 0: a pair walks all N tiles of a row block
@@ -233,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (p.load_evict_first & 1) tma_load_2d_2cta_hint(sa, &map_a, lead_full, kb * kBK, m_blk * kBM, l2_policy_evict_first());
                 else tma_load_2d_2cta(sa, &map_a, lead_full, kb * kBK, m_blk * kBM);
               }
-              if (p.dbg & 64) tma_load_2d_2cta_hint(sa + (ARES ? 0 : kATileBytes), &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * b_half, l2_policy_evict_last());
+              if ((p.dbg & 64) || (p.load_evict_first & 4)) tma_load_2d_2cta_hint(sa + (ARES ? 0 : kATileBytes), &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * b_half, l2_policy_evict_last());
               else tma_load_2d_2cta(sa + (ARES ? 0 : kATileBytes), &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * b_half);
             }
           }

@@ -161,7 +161,7 @@ struct LdmHandle {
   // replayed; everything that changes from call to call lives in device memory (noise key block, staged cond / start ids)
   int use_graph = 1;           // env LDM_GRAPH=0: plain stream launches
   int sweep = 1;               // env LDM_SWEEP=0: every kernel walks its row blocks in ascending order (no alternating directions)
-  int l2_hint = 1;             // env LDM_L2_HINT bit mask: L2 evict_last hint on the 16-bit stores of 1 = QKV / FF1, 2 = attention, 4 = out-projection (z16), 8 = FF2 (x16 / z16); evict_first hint on loads of data that is dead afterwards: 16 = A operands of QKV / FF1 / out-projection, 32 = fp32 residual blocks, 64 = attention's Q / K / V; 0 = none
+  int l2_hint = 1;             // env LDM_L2_HINT bit mask: L2 evict_last hint on the 16-bit stores of 1 = QKV / FF1, 2 = attention, 4 = out-projection (z16), 8 = FF2 (x16 / z16); evict_first hint on loads of data that is dead afterwards: 16 = A operands of QKV / FF1 / out-projection, 32 = fp32 residual blocks, 64 = attention's Q / K / V; 128 = evict_last on the weight tiles; 0 = none
   int fuse_embed = 1;          // env LDM_FUSE_EMBED=0: the loop launches the embedding kernel in every step instead of fusing it into the previous draw
   cudaStream_t cap_stream = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
@@ -371,7 +371,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
   for (int l = 0; l < L; ++l) {
     {  // QKV projection (+bias, q * 1/sqrt(head_dim))
       GemmParams p{M, kQkvN, d, kQkvN / 256, h->bqkv[l], h->qkv16, kQkvN, 1.0f / sqrtf(static_cast<float>(d / h->desc.n_heads)), 8 * kHeadPad};
-      p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles); p.rev = next_rev(); p.store_evict_last = h->l2_hint & 1; p.load_evict_first = (h->l2_hint & 16) ? 1 : 0;
+      p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles); p.rev = next_rev(); p.store_evict_last = h->l2_hint & 1; p.load_evict_first = ((h->l2_hint & 16) ? 1 : 0) | ((h->l2_hint & 128) ? 4 : 0);
       ProfScope ps(h, CAT_QKV, st);
       CK(launch_step(h, gemm_tc_kernel<256, 256, kAresStages, EPI_QKV, BF16, true>, pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, kAresStages, EPI_QKV, true>::kBytes, st, false,
                      h->m_x16, h->m_wqkv[l], h->b_qkv16, h->b_qkv16, h->b_qkv16, h->t_x16, p));
@@ -385,7 +385,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     LDM_STAGE_DONE();
     {  // out-projection + bias + residual (from the NORMALISED x) -> y32 ; z16 = LayerNorm2(y)   [fused epilogue]
       GemmParams p{M, d, kAttN, 2, h->bo[l], h->z16, d, 1.0f, 0, h->x32, h->y32, h->ln2w[l], h->ln2b[l], 0, nullptr};
-      p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch; p.rev = next_rev(); p.store_evict_last = (h->l2_hint & 4) ? 1 : 0; p.load_evict_first = ((h->l2_hint & 16) ? 1 : 0) | ((h->l2_hint & 32) ? 2 : 0);
+      p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch; p.rev = next_rev(); p.store_evict_last = (h->l2_hint & 4) ? 1 : 0; p.load_evict_first = ((h->l2_hint & 16) ? 1 : 0) | ((h->l2_hint & 32) ? 2 : 0) | ((h->l2_hint & 128) ? 4 : 0);
       ProfScope ps(h, CAT_OUTPROJ, st);
       CK(launch_step(h, gemm_tc_kernel<224, 240, 3, EPI_LN, BF16>, ln_grid, kGemmThreads, GemmSmem<240, 3, EPI_LN>::kBytes, st, true,
                      h->m_att16, h->m_wo[l], h->b_z16, h->b_x32, h->b_y32, h->b_y32, p));
@@ -393,7 +393,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
     LDM_STAGE_DONE();
     {  // FF1 + ReLU
       GemmParams p{M, ff, d, (ff + 255) / 256, h->b1[l], h->hid16, ff, 1.0f, 0};   // 7 tiles of 256 columns + one of 64
-      p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles); p.rev = next_rev(); p.store_evict_last = h->l2_hint & 1; p.load_evict_first = (h->l2_hint & 16) ? 1 : 0;
+      p.dbg = h->gemm_dbg; p.tile_sched = tile_sched(p.n_tiles); p.rev = next_rev(); p.store_evict_last = h->l2_hint & 1; p.load_evict_first = ((h->l2_hint & 16) ? 1 : 0) | ((h->l2_hint & 128) ? 4 : 0);
       ProfScope ps(h, CAT_FF1, st);
       CK(launch_step(h, gemm_tc_kernel<256, 256, kAresStages, EPI_RELU, BF16, true>, pair_grid(p.n_tiles), kGemmThreads, GemmSmem<256, kAresStages, EPI_RELU, true>::kBytes, st, false,
                      h->m_z16, h->m_w1[l], h->b_hid16, h->b_hid16, h->b_hid16, h->t_z16, p));
@@ -409,7 +409,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       } else {
         p.ln_scale = h->hlnw; p.ln_shift = h->hlnb; p.adaln = 0; p.out32 = nullptr; p.out = h->z16;
       }
-      p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch; p.rev = next_rev(); p.store_evict_last = (h->l2_hint & 8) ? 1 : 0; p.load_evict_first = (h->l2_hint & 32) ? 2 : 0;   // hid16 is read by two pairs: no hint on the A tiles
+      p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch; p.rev = next_rev(); p.store_evict_last = (h->l2_hint & 8) ? 1 : 0; p.load_evict_first = ((h->l2_hint & 32) ? 2 : 0) | ((h->l2_hint & 128) ? 4 : 0);   // hid16 is read by two pairs: no hint on the A tiles
       ProfScope ps(h, CAT_FF2, st);
       CK(launch_step(h, gemm_tc_kernel<224, 240, 5, EPI_LN, BF16>, ln_grid, kGemmThreads, GemmSmem<240, 5, EPI_LN>::kBytes, st, true,
                      h->m_hid16, h->m_w2[l], *mo, h->b_y32, h->b_x32, h->b_x32, p));
