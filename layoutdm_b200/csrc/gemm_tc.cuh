@@ -232,6 +232,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               mbar_arrive_expect_tx_cluster(lead_full, SM::kStageBytes);
               if constexpr (!ARES) {
                 if (p.load_evict_first & 1) tma_load_2d_2cta_hint(sa, &map_a, lead_full, kb * kBK, m_blk * kBM, l2_policy_evict_first());
+                else if (p.load_evict_first & 8) tma_load_2d_2cta_hint(sa, &map_a, lead_full, kb * kBK, m_blk * kBM, l2_policy_evict_last());   // read again by the partner pair
                 else tma_load_2d_2cta(sa, &map_a, lead_full, kb * kBK, m_blk * kBM);
               }
               if ((p.dbg & 64) || (p.load_evict_first & 4)) tma_load_2d_2cta_hint(sa + (ARES ? 0 : kATileBytes), &map_b, lead_full, kb * kBK, n_blk * BN_STORE + static_cast<int>(cta_rank) * b_half, l2_policy_evict_last());

@@ -409,7 +409,7 @@ int launch_denoiser(LdmHandle* h, int n, const long long* ids_in, int t_model, c
       } else {
         p.ln_scale = h->hlnw; p.ln_shift = h->hlnb; p.adaln = 0; p.out32 = nullptr; p.out = h->z16;
       }
-      p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch; p.rev = next_rev(); p.store_evict_last = (h->l2_hint & 8) ? 1 : 0; p.load_evict_first = ((h->l2_hint & 32) ? 2 : 0) | ((h->l2_hint & 128) ? 4 : 0);   // hid16 is read by two pairs: no hint on the A tiles
+      p.dbg = h->gemm_dbg; p.tile_sched = 1; p.ln_stats = h->ln_stats; p.ln_epoch = ++h->ln_epoch; p.rev = next_rev(); p.store_evict_last = (h->l2_hint & 8) ? 1 : 0; p.load_evict_first = ((h->l2_hint & 32) ? 2 : 0) | ((h->l2_hint & 128) ? 4 : 0) | ((h->l2_hint & 256) ? 8 : 0);   // hid16 is read by two pairs: never evict_first; 256 = evict_last
       ProfScope ps(h, CAT_FF2, st);
       CK(launch_step(h, gemm_tc_kernel<224, 240, 5, EPI_LN, BF16>, ln_grid, kGemmThreads, GemmSmem<240, 5, EPI_LN>::kBytes, st, true,
                      h->m_hid16, h->m_w2[l], *mo, h->b_y32, h->b_x32, h->b_x32, p));
