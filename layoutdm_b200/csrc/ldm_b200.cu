@@ -801,18 +801,25 @@ int ldm_sample_loop(LdmHandle* h, int32_t B, int32_t n_steps, const int32_t* t_m
     if (h->graph_exec) { CK(cudaStreamSynchronize(st)); cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // no replay of the old plan may still be running
     if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
     const int64_t l0 = h->launches;
-    CK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-    rc = run_loop(h, B, n_steps, t_model, t_post, has_cond ? &gc : nullptr, sampling, 0, 0, ids_init ? h->ids[1] : nullptr, h->ids_final, nullptr,
-                  h->cap_stream, h->call_block);
+    // any failure to record or instantiate the plan (e.g. a capture conflict in the host application) permanently falls back to plain
+    // stream launches for this handle instead of failing the call
+    bool ok = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     cudaGraph_t g = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &g);
-    h->graph_launches = h->launches - l0;
-    h->launches = l0;                                  // counted per replay below
-    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-    if (ce != cudaSuccess || !g) return fail(LDM_ERR_CUDA, "graph capture of the sampling loop failed: %s", cudaGetErrorString(ce));
-    const cudaError_t ie = cudaGraphInstantiate(&h->graph_exec, g, 0);
-    cudaGraphDestroy(g);
-    if (ie != cudaSuccess) { h->graph_exec = nullptr; return fail(LDM_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+    if (ok) {
+      rc = run_loop(h, B, n_steps, t_model, t_post, has_cond ? &gc : nullptr, sampling, 0, 0, ids_init ? h->ids[1] : nullptr, h->ids_final, nullptr,
+                    h->cap_stream, h->call_block);
+      ok = cudaStreamEndCapture(h->cap_stream, &g) == cudaSuccess && g != nullptr && rc == LDM_OK;
+      h->graph_launches = h->launches - l0;
+      h->launches = l0;                                  // counted per replay below
+    }
+    if (ok) ok = cudaGraphInstantiate(&h->graph_exec, g, 0) == cudaSuccess;
+    if (g) cudaGraphDestroy(g);
+    if (!ok) {
+      cudaGetLastError();
+      h->graph_exec = nullptr; h->use_graph = 0;
+      return run_loop(h, B, n_steps, t_model, t_post, has_cond ? &gc : nullptr, sampling, seed, b_global0, ids_init ? h->ids[1] : nullptr,
+                      reinterpret_cast<long long*>(ids_out), nullptr, st, nullptr);
+    }
     h->graph_key = key;
   }
   CK(cudaGraphLaunch(h->graph_exec, st));
