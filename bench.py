@@ -428,13 +428,6 @@ def run_b200_arm(args, world, rank, local):
         dts = [arm.step(1 + k) for k in range(3)]                 # ~15 s of CPU work in total
         dt = sum(dts) / len(dts)
         cpu = {"value": arm.layouts_per_s(dt), "unit": UNIT, "cores": cores, "kind": arm.kind, "sample": arm.sample_desc(dt) + f"; mean of {len(dts)} steps after 1 warm-up"}
-        if arm.kind == "reference":                               # also the single-thread number (4 of the 100 iterations, scaled)
-            torch.set_num_threads(1)
-            arm.cfg = arm.rh.sampling_cfg("random", num_timesteps=4)
-            arm.step(50)
-            d1 = arm.step(51)
-            cpu["single_thread"] = {"value": REF_B / (d1 * T / 4), "unit": UNIT, "sample": f"{REF_B} layouts x 4 of {T} iterations ({d1:.1f} s), scaled x{T / 4:.0f}"}
-            torch.set_num_threads(cores)
         gpu_eager = gpu_eager_reference(B, dev)
         if gpu_eager:
             gpu_eager["speedup_e2e"] = e2e["value"] / gpu_eager["value"]
