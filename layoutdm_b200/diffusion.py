@@ -355,10 +355,12 @@ class LayoutDMB200:
         ids = self.model.sample(batch_size=batch_size, cond=cond, sampling_cfg=sampling_cfg, **kw)
         if self.tokenizer is not None:
             return self.tokenizer.decode(ids)
-        if kwargs.get("decode_on_device", False) and not kw.get("get_intermediate_results", False):
+        if kw.get("get_intermediate_results", False):
+            return ids                                             # the list of per-step ids, like the core's sample()
+        if kwargs.get("decode_on_device", True):                   # ids -> layouts on the GPU (ldm_decode), results back on the CPU like layoutdm.py:87
             c = None if self._centers is None else torch.stack([torch.as_tensor(x, dtype=torch.float32).view(-1) for x in self._centers])
             return {k: v.cpu() for k, v in self.model.engine.decode(ids, c).items()}
-        return decode_ids(ids, self.vocab, self._centers)
+        return decode_ids(ids, self.vocab, self._centers)          # host fallback (decode_on_device=False)
 
     def get_cond(self, label: torch.Tensor, bbox: torch.Tensor, mask: torch.Tensor, cond_type: str = "c", refine: Optional[dict] = None) -> Dict:
         """helpers/task.py:get_cond (:27-151) for dense layouts (what `sparse_to_dense(batch)` returns: bbox (B,E,4), label (B,E),
